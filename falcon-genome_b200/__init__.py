@@ -1,0 +1,4 @@
+"""falcon-genome_b200 — B200-native PairHMM forward-likelihood path for fcs-genome's
+HaplotypeCaller / Mutect2 stages (C ABI library + thin host mirror).  See DESIGN.md."""
+from .batch import FlatBatch, Region, partition_regions  # noqa: F401
+from .pairhmm import PairHMM, PairHMMError, RegionArray, ResidentBatch, kernel_class  # noqa: F401

@@ -1,0 +1,835 @@
+// phmm_engine.cu — packer (batcher), per-device chunk pipeline, multi-GPU dispatcher.
+//
+// The reference fans HaplotypeCaller / Mutect2 out as independent processes per genome
+// partition (/root/reference/src/worker-htc.cpp:113-145, src/Executor.cpp:50-108); every
+// active region, read and haplotype pair is independent, so here regions are partitioned
+// over the devices by cell count with no device-to-device exchange.
+//
+// Per device, `slots` chunk pipelines run concurrently on their own streams:
+//   host pack (pinned) -> H2D -> FP32 wavefront kernels (one launch per kernel class)
+//   -> FP64 rerun kernels (drain the per-class queues the FP32 kernels filled) -> D2H
+//   -> host scatter into the caller's out_log10.
+// Packing chunk k+1 overlaps the GPU work of chunk k.
+#include "phmm_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "phmm_luts.h"
+
+namespace fcsphmm {
+
+// ---------------------------------------------------------------------------------------
+// error text (thread local, as the ABI promises)
+static thread_local std::string g_err;
+int set_error(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+const char* last_error() { return g_err.c_str(); }
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return set_error(FCS_PHMM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int64_t env_i64(const char* name, int64_t dflt) {
+  const char* v = std::getenv(name);
+  if (!v || !*v) return dflt;
+  return std::strtoll(v, nullptr, 10);
+}
+
+// f32 / f64 class ids = position among the f32 / f64 entries of the kernel table
+static std::vector<const KernelEntry*> g_f32_classes, g_f64_classes;
+static std::once_flag g_cls_once;
+static void build_class_lists() {
+  for (const KernelEntry* k = kernel_table(); k->G != 0; ++k) (k->f64 ? g_f64_classes : g_f32_classes).push_back(k);
+}
+static int class_id(const KernelEntry* k) {
+  const auto& v = k->f64 ? g_f64_classes : g_f32_classes;
+  for (size_t i = 0; i < v.size(); ++i)
+    if (v[i] == k) return (int)i;
+  return -1;
+}
+
+int ChunkPlan::launches() const {
+  int n = 0;
+  if (!force_double)
+    for (const auto& r : f32) n += r.n_tasks ? 1 : 0;
+  for (const auto& r : f64) n += r.cap ? 1 : 0;
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------
+int Engine::create(const fcs_phmm_config* cfg, Engine** out) {
+  *out = nullptr;
+  std::unique_ptr<Engine> e(new Engine());
+  int rc = e->init(cfg);
+  if (rc != FCS_PHMM_OK) return rc;
+  *out = e.release();
+  return FCS_PHMM_OK;
+}
+
+int Engine::init(const fcs_phmm_config* cfg) {
+  std::call_once(g_cls_once, build_class_lists);
+  if ((int)g_f64_classes.size() > kMaxF64Classes) return set_error(FCS_PHMM_EINVAL, "too many FP64 kernel classes compiled in");
+  fcs_phmm_config c;
+  std::memset(&c, 0, sizeof(c));
+  if (cfg) std::memcpy(&c, cfg, std::min<size_t>(sizeof(c), cfg->struct_size ? cfg->struct_size : sizeof(c)));
+  use_double_ = c.use_double != 0;
+  keep_raw_ = c.keep_raw_f32 != 0;
+  pack_threads_ = c.max_threads;
+  max_chunk_cells_ = c.max_chunk_cells > 0 ? c.max_chunk_cells : env_i64("FCS_PHMM_CHUNK_CELLS", 3000000000LL);
+  int nslots = c.slots_per_device > 0 ? c.slots_per_device : 3;
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return set_error(FCS_PHMM_ENODEV, std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") +
+                                          " (libfcs_pairhmm has no CPU fallback)");
+  std::vector<int> ords;
+  if (c.n_devices > 0) {
+    for (int i = 0; i < c.n_devices; ++i) ords.push_back(c.devices ? c.devices[i] : i);
+  } else {
+    for (int i = 0; i < ndev; ++i) ords.push_back(i);
+  }
+  const Luts& L = luts();
+  for (int ord : ords) {
+    if (ord < 0 || ord >= ndev) return set_error(FCS_PHMM_EINVAL, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ord));
+    if (prop.major != 10)
+      return set_error(FCS_PHMM_ENODEV, std::string("device ") + std::to_string(ord) + " (" + prop.name + ") is sm_" +
+                                            std::to_string(prop.major * 10 + prop.minor) + "; the kernels are built for sm_100a only");
+    std::unique_ptr<Device> d(new Device());
+    d->ordinal = ord;
+    d->sm_count = prop.multiProcessorCount;
+    CK(cudaSetDevice(ord));
+    CK(cudaMalloc(&d->d_ph2pr_f, sizeof(L.ph2pr_f)));
+    CK(cudaMalloc(&d->d_mm_f, sizeof(L.mm_f)));
+    CK(cudaMalloc(&d->d_ph2pr_d, sizeof(L.ph2pr_d)));
+    CK(cudaMalloc(&d->d_mm_d, sizeof(L.mm_d)));
+    CK(cudaMemcpy(d->d_ph2pr_f, L.ph2pr_f, sizeof(L.ph2pr_f), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d->d_mm_f, L.mm_f, sizeof(L.mm_f), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d->d_ph2pr_d, L.ph2pr_d, sizeof(L.ph2pr_d), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d->d_mm_d, L.mm_d, sizeof(L.mm_d), cudaMemcpyHostToDevice));
+    for (const KernelEntry* k = kernel_table(); k->G != 0; ++k) CK(k->set_max_smem(prop.sharedMemPerBlockOptin));
+    d->slots.resize(nslots);
+    for (Slot& s : d->slots) {
+      CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      CK(cudaEventCreate(&s.ev_k0));
+      CK(cudaEventCreate(&s.ev_k1));
+      CK(cudaEventCreate(&s.ev_k2));
+      CK(cudaEventCreate(&s.ev_done));
+    }
+    devs_.push_back(std::move(d));
+  }
+  return FCS_PHMM_OK;
+}
+
+static void free_slot(Slot& s) {
+  if (s.stream) cudaStreamSynchronize(s.stream);
+  if (s.h_in) cudaFreeHost(s.h_in);
+  if (s.h_out) cudaFreeHost(s.h_out);
+  if (s.d_buf) cudaFree(s.d_buf);
+  if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+  if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+  if (s.ev_k2) cudaEventDestroy(s.ev_k2);
+  if (s.ev_done) cudaEventDestroy(s.ev_done);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s = Slot();
+}
+
+Engine::~Engine() {
+  {
+    std::lock_guard<std::mutex> lk(tickets_mu_);
+    for (auto& kv : tickets_)
+      if (kv.second->th.joinable()) kv.second->th.join();
+    tickets_.clear();
+  }
+  for (auto& d : devs_) {
+    cudaSetDevice(d->ordinal);
+    for (Slot& s : d->slots) free_slot(s);
+    cudaFree(d->d_ph2pr_f);
+    cudaFree(d->d_mm_f);
+    cudaFree(d->d_ph2pr_d);
+    cudaFree(d->d_mm_d);
+  }
+}
+
+int Engine::ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t dev_bytes) {
+  auto grow = [](size_t need) { return align_up(need + need / 4 + 4096, 4096); };
+  if (in_bytes > s.h_in_cap) {
+    if (s.h_in) CK(cudaFreeHost(s.h_in));
+    s.h_in = nullptr;
+    s.h_in_cap = grow(in_bytes);
+    if (cudaHostAlloc((void**)&s.h_in, s.h_in_cap, cudaHostAllocDefault) != cudaSuccess) {
+      s.h_in_cap = 0;
+      return set_error(FCS_PHMM_ENOMEM, "pinned host allocation failed");
+    }
+  }
+  if (out_bytes > s.h_out_cap) {
+    if (s.h_out) CK(cudaFreeHost(s.h_out));
+    s.h_out = nullptr;
+    s.h_out_cap = grow(out_bytes);
+    if (cudaHostAlloc((void**)&s.h_out, s.h_out_cap, cudaHostAllocDefault) != cudaSuccess) {
+      s.h_out_cap = 0;
+      return set_error(FCS_PHMM_ENOMEM, "pinned host allocation failed");
+    }
+  }
+  if (dev_bytes > s.d_cap) {
+    if (s.d_buf) CK(cudaFree(s.d_buf));
+    s.d_buf = nullptr;
+    s.d_cap = grow(dev_bytes);
+    if (cudaMalloc((void**)&s.d_buf, s.d_cap) != cudaSuccess) {
+      s.d_cap = 0;
+      return set_error(FCS_PHMM_ENOMEM, "device allocation failed");
+    }
+  }
+  return FCS_PHMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 1: choose the regions of the chunk, order each region's reads by length, cut the
+// (read group x haplotype run) tasks per kernel class and size every section.
+namespace {
+
+struct Planner {
+  const Input& in;
+  Slot& s;
+  bool force_double;
+  bool keep_raw;
+  int64_t max_cells;
+  uint32_t hs_cols;  // haplotype columns per task (bounds the shared-memory stream)
+
+  int run(const std::vector<int64_t>& regions, size_t first, size_t& next) {
+    ChunkPlan& P = s.plan;
+    P = ChunkPlan();
+    P.force_double = force_double;
+    s.class_tasks.resize(g_f32_classes.size());
+    for (auto& v : s.class_tasks) v.clear();
+    s.order.clear();
+    std::vector<uint32_t> f32_hs(g_f32_classes.size(), 0), f32_stage(g_f32_classes.size(), 0);
+    std::vector<uint32_t> f64_cap(g_f64_classes.size(), 0), f64_maxlh(g_f64_classes.size(), 0);
+    size_t reads_bytes = 0, haps_bytes = 0;
+    std::vector<uint32_t> lens, hlens;
+    size_t k = first;
+    for (; k < regions.size(); ++k) {
+      const int64_t g = regions[k];
+      int32_t nr = 0, nh = 0;
+      in.shape(g, nr, nh);
+      if (nr < 0 || nh < 0) return set_error(FCS_PHMM_EINVAL, "negative read or haplotype count");
+      if (nr == 0 || nh == 0) {  // nothing to compute; keep the slot so scatter stays aligned
+        P.regions.push_back(g);
+        P.reg_out0.push_back(P.n_pairs);
+        continue;
+      }
+      if (!in.out(g)) return set_error(FCS_PHMM_EINVAL, "out_log10 is null");
+      lens.resize(nr);
+      hlens.resize(nh);
+      uint64_t sum_r = 0, sum_h = 0;
+      size_t rb = 0, hb = 0;
+      for (int32_t i = 0; i < nr; ++i) {
+        const InRead r = in.read(g, i);
+        if (r.len <= 0 || !r.b || !r.q || !r.i || !r.d || !r.c)
+          return set_error(FCS_PHMM_EINVAL, "read with non-positive length or null array");
+        if (!select_kernel(false, r.len) || !select_kernel(true, r.len))
+          return set_error(FCS_PHMM_EUNSUPPORTED, "read length " + std::to_string(r.len) + " exceeds the compiled kernel classes");
+        lens[i] = (uint32_t)r.len;
+        sum_r += (uint64_t)r.len;
+        rb += 5u * round_up16((uint32_t)r.len);
+      }
+      for (int32_t j = 0; j < nh; ++j) {
+        const InHap h = in.hap(g, j);
+        if (h.len <= 0 || !h.b) return set_error(FCS_PHMM_EINVAL, "haplotype with non-positive length or null array");
+        if (h.len > FCS_PHMM_MAX_HAP_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype longer than FCS_PHMM_MAX_HAP_LEN");
+        hlens[j] = (uint32_t)h.len;
+        sum_h += (uint64_t)h.len;
+        hb += round_up16((uint32_t)h.len);
+      }
+      const uint64_t cells = sum_r * sum_h;
+      const uint64_t pairs = (uint64_t)nr * (uint64_t)nh;
+      if (!P.regions.empty() && P.cells > 0 &&
+          ((int64_t)(P.cells + cells) > max_cells || P.n_pairs + pairs > 0x7fffffffULL ||
+           reads_bytes + rb + haps_bytes + hb > (size_t)1 << 31))
+        break;
+      if (pairs > 0x7fffffffULL) return set_error(FCS_PHMM_EUNSUPPORTED, "region with more than 2^31 pairs");
+      // ---- reads sorted by length (descending, stable) so a lane group shares a class
+      const size_t ord0 = s.order.size();
+      s.order.resize(ord0 + nr);
+      uint32_t* ord = s.order.data() + ord0;
+      std::iota(ord, ord + nr, 0u);
+      bool same = true;
+      for (int32_t i = 1; i < nr && same; ++i) same = lens[i] == lens[0];
+      if (!same) std::stable_sort(ord, ord + nr, [&](uint32_t a, uint32_t b) { return lens[a] > lens[b]; });
+      // ---- tasks
+      const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
+      for (int32_t i = 0; i < nr;) {
+        const KernelEntry* kc = select_kernel(false, (int)lens[ord[i]]);
+        const int cid = class_id(kc);
+        const int NG = 32 / kc->G;
+        const int cnt = std::min<int32_t>(NG, nr - i);
+        for (int32_t j = 0; j < nh;) {
+          uint32_t cols = 0, stage = 0;
+          int32_t j1 = j;
+          while (j1 < nh && (j1 == j || cols + hlens[j1] + (kc->G - 1) <= hs_cols) && (j1 - j) < 0xffff) {
+            cols += hlens[j1] + (kc->G - 1);
+            stage += round_up16(hlens[j1]);
+            ++j1;
+          }
+          cols += (kc->G - 1);
+          Task t;
+          t.read0 = read_base + (uint32_t)i;
+          t.hap0 = hap_base + (uint32_t)j;
+          t.n_reads = (uint16_t)cnt;
+          t.n_haps = (uint16_t)(j1 - j);
+          t.reserved = 0;
+          s.class_tasks[cid].push_back(t);
+          f32_hs[cid] = std::max(f32_hs[cid], cols);
+          f32_stage[cid] = std::max(f32_stage[cid], stage);
+          j = j1;
+        }
+        i += cnt;
+      }
+      // ---- FP64 queue capacity per class (worst case: every pair of the read falls back)
+      uint32_t maxlh = 0;
+      for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
+      for (int32_t i = 0; i < nr; ++i) {
+        const int c64 = class_id(select_kernel(true, (int)lens[i]));
+        f64_cap[c64] += (uint32_t)nh;
+        f64_maxlh[c64] = std::max(f64_maxlh[c64], maxlh);
+      }
+      P.regions.push_back(g);
+      P.reg_out0.push_back(P.n_pairs);
+      P.n_reads += nr;
+      P.n_haps += nh;
+      P.n_pairs += pairs;
+      P.cells += cells;
+      reads_bytes += rb;
+      haps_bytes += hb;
+    }
+    next = k;
+    // ---- layout
+    size_t off = 0;
+    P.off_reads = off; off = align_up(off + reads_bytes, 256);
+    P.off_haps = off; off = align_up(off + haps_bytes, 256);
+    P.off_rmeta = off; off = align_up(off + P.n_reads * sizeof(ReadMeta), 256);
+    P.off_hmeta = off; off = align_up(off + P.n_haps * sizeof(HapMeta), 256);
+    P.off_tasks = off;
+    P.n_tasks = 0;
+    for (size_t c = 0; c < s.class_tasks.size(); ++c) {
+      if (s.class_tasks[c].empty()) continue;
+      F32Range r;
+      r.k = g_f32_classes[c];
+      r.task0 = (uint32_t)P.n_tasks;
+      r.n_tasks = (uint32_t)s.class_tasks[c].size();
+      r.hs_cap = f32_hs[c];
+      r.hap_stage = f32_stage[c];
+      P.f32.push_back(r);
+      P.n_tasks += r.n_tasks;
+    }
+    off = align_up(off + P.n_tasks * sizeof(Task), 256);
+    P.off_rbase = off; off += kMaxF64Classes * sizeof(uint32_t);
+    P.off_rcount = off; off += kMaxF64Classes * sizeof(uint32_t);
+    off = align_up(off, 256);
+    P.off_rerun = off;
+    for (size_t c = 0; c < g_f64_classes.size(); ++c) {
+      if (!f64_cap[c]) continue;
+      F64Range r;
+      r.k = g_f64_classes[c];
+      r.cls = (uint32_t)c;
+      r.cap = f64_cap[c];
+      r.hs_cap = f64_maxlh[c] + 2u * (uint32_t)(r.k->G - 1);
+      r.hap_stage = round_up16(f64_maxlh[c]);
+      P.f64.push_back(r);
+    }
+    const size_t rerun_bytes = align_up(P.n_pairs * sizeof(RerunEntry), 256);
+    if (force_double) { off += rerun_bytes; P.in_bytes = off; }
+    else { P.in_bytes = off; off += rerun_bytes; }
+    P.off_out = off; off += P.n_pairs * sizeof(double);
+    P.off_raw = off; if (keep_raw) off += P.n_pairs * sizeof(float);
+    P.off_used = off; off += P.n_pairs;
+    P.total_bytes = align_up(off, 256);
+    return FCS_PHMM_OK;
+  }
+};
+
+}  // namespace
+
+static const uint8_t* hap_valid_lut() {
+  static uint8_t lut[256];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    std::memset(lut, 0, sizeof(lut));
+    lut[(int)'A'] = lut[(int)'C'] = lut[(int)'G'] = lut[(int)'T'] = lut[(int)'N'] = 1;
+  });
+  return lut;
+}
+
+// Pass 2: copy reads / quals / haplotypes into the pinned staging buffer in device layout.
+int Engine::pack_chunk(Slot& s, const Input& in) {
+  ChunkPlan& P = s.plan;
+  uint8_t* base = s.h_in;
+  ReadMeta* rmeta = reinterpret_cast<ReadMeta*>(base + P.off_rmeta);
+  HapMeta* hmeta = reinterpret_cast<HapMeta*>(base + P.off_hmeta);
+  uint32_t* rbase = reinterpret_cast<uint32_t*>(base + P.off_rbase);
+  uint32_t* rcount = reinterpret_cast<uint32_t*>(base + P.off_rcount);
+  RerunEntry* rerun = P.force_double ? reinterpret_cast<RerunEntry*>(base + P.off_rerun) : nullptr;
+  std::memset(rbase, 0, kMaxF64Classes * sizeof(uint32_t));
+  std::memset(rcount, 0, kMaxF64Classes * sizeof(uint32_t));
+  {
+    uint32_t acc = 0;
+    for (const F64Range& r : P.f64) { rbase[r.cls] = acc; acc += r.cap; }
+  }
+  std::vector<uint32_t> fill(kMaxF64Classes, 0);
+  const uint8_t* valid = hap_valid_lut();
+  size_t rpos = 0, hpos = 0, ridx = 0, hidx = 0, opos = 0;
+  for (size_t k = 0; k < P.regions.size(); ++k) {
+    const int64_t g = P.regions[k];
+    int32_t nr = 0, nh = 0;
+    in.shape(g, nr, nh);
+    if (nr == 0 || nh == 0) continue;
+    const uint32_t hap0 = (uint32_t)hidx;
+    for (int32_t j = 0; j < nh; ++j) {
+      const InHap h = in.hap(g, j);
+      uint8_t* dst = base + P.off_haps + hpos;
+      const uint32_t lp = round_up16((uint32_t)h.len);
+      std::memcpy(dst, h.b, (size_t)h.len);
+      std::memset(dst + h.len, 'N', lp - (uint32_t)h.len);
+      uint8_t ok = 1;
+      for (int32_t x = 0; x < h.len; ++x) ok &= valid[h.b[x]];
+      if (!ok) return set_error(FCS_PHMM_EINVAL, "haplotype contains a byte outside ACGTN");
+      hmeta[hidx].data_off16 = (uint32_t)(hpos / 16);
+      hmeta[hidx].len = (uint32_t)h.len;
+      hpos += lp;
+      ++hidx;
+    }
+    const uint32_t* ord = s.order.data() + opos;
+    for (int32_t i = 0; i < nr; ++i) {
+      const uint32_t oi = ord[i];
+      const InRead r = in.read(g, (int32_t)oi);
+      const uint32_t lp = round_up16((uint32_t)r.len);
+      uint8_t* dst = base + P.off_reads + rpos;
+      const uint8_t* src[5] = {r.b, r.q, r.i, r.d, r.c};
+      for (int pl = 0; pl < 5; ++pl) {
+        std::memcpy(dst + (size_t)pl * lp, src[pl], (size_t)r.len);
+        std::memset(dst + (size_t)pl * lp + r.len, 0, lp - (uint32_t)r.len);
+      }
+      const int c64 = class_id(select_kernel(true, r.len));
+      ReadMeta& m = rmeta[ridx];
+      m.data_off16 = (uint32_t)(rpos / 16);
+      m.len_cls = (uint32_t)r.len | ((uint32_t)c64 << 24);
+      m.out_off = (uint32_t)(P.reg_out0[k] + (uint64_t)oi * (uint64_t)nh);
+      m.hap0 = hap0;
+      if (rerun) {
+        RerunEntry* e = rerun + rbase[c64] + fill[c64];
+        for (int32_t j = 0; j < nh; ++j) { e[j].read = (uint32_t)ridx; e[j].hap = hap0 + (uint32_t)j; }
+        fill[c64] += (uint32_t)nh;
+      }
+      rpos += 5u * (size_t)lp;
+      ++ridx;
+    }
+    opos += nr;
+  }
+  if (rerun)
+    for (const F64Range& r : P.f64) rcount[r.cls] = fill[r.cls];
+  Task* tasks = reinterpret_cast<Task*>(base + P.off_tasks);
+  for (const F32Range& r : P.f32) {
+    const int cid = class_id(r.k);
+    std::memcpy(tasks + r.task0, s.class_tasks[cid].data(), (size_t)r.n_tasks * sizeof(Task));
+  }
+  return FCS_PHMM_OK;
+}
+
+void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) const {
+  const ChunkPlan& P = s.plan;
+  uint8_t* b = s.d_buf;
+  p.reads = b + P.off_reads;
+  p.haps = b + P.off_haps;
+  p.rmeta = reinterpret_cast<const ReadMeta*>(b + P.off_rmeta);
+  p.hmeta = reinterpret_cast<const HapMeta*>(b + P.off_hmeta);
+  p.tasks = reinterpret_cast<const Task*>(b + P.off_tasks);
+  p.n_tasks = 0;
+  p.ph2pr = f64 ? d.d_ph2pr_d : d.d_ph2pr_f;
+  p.mm = f64 ? d.d_mm_d : d.d_mm_f;
+  p.out = reinterpret_cast<double*>(b + P.off_out);
+  p.used_fp64 = b + P.off_used;
+  p.raw_f32 = keep_raw_ ? reinterpret_cast<float*>(b + P.off_raw) : nullptr;
+  p.rerun = reinterpret_cast<RerunEntry*>(b + P.off_rerun);
+  p.rerun_count = reinterpret_cast<uint32_t*>(b + P.off_rcount);
+  p.rerun_base = reinterpret_cast<const uint32_t*>(b + P.off_rbase);
+  p.f64_class = 0;
+  p.hs_cap = 0;
+  p.hap_stage_bytes = 0;
+}
+
+// Enqueue one chunk on the slot's stream.  upload/download = include the H2D / D2H copies.
+int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
+  const ChunkPlan& P = s.plan;
+  if (upload && P.in_bytes) {
+    CK(cudaMemcpyAsync(s.d_buf, s.h_in, P.in_bytes, cudaMemcpyHostToDevice, s.stream));
+    stats_.h2d += P.in_bytes;
+  }
+  if (!upload && !P.force_double)  // resident batch: the queues must start empty on every run
+    CK(cudaMemsetAsync(s.d_buf + P.off_rcount, 0, kMaxF64Classes * sizeof(uint32_t), s.stream));
+  CK(cudaEventRecord(s.ev_k0, s.stream));
+  if (!P.force_double) {
+    for (const F32Range& r : P.f32) {
+      if (!r.n_tasks) continue;
+      KParams p;
+      fill_kparams(d, s, p, false);
+      p.tasks += r.task0;
+      p.n_tasks = r.n_tasks;
+      p.hs_cap = r.hs_cap;
+      p.hap_stage_bytes = r.hap_stage;
+      const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
+      if (smem > 227 * 1024)
+        return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype run does not fit in shared memory (" + std::to_string(smem) + " bytes)");
+      CK(r.k->launch(p, r.n_tasks, smem, s.stream));
+      stats_.launches += 1;
+    }
+  }
+  CK(cudaEventRecord(s.ev_k1, s.stream));
+  for (const F64Range& r : P.f64) {
+    if (!r.cap) continue;
+    KParams p;
+    fill_kparams(d, s, p, true);
+    p.f64_class = r.cls;
+    p.hs_cap = r.hs_cap;
+    p.hap_stage_bytes = r.hap_stage;
+    const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
+    if (smem > 227 * 1024)
+      return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype too long for the FP64 kernel's shared memory (" + std::to_string(smem) + " bytes)");
+    const unsigned ng = 32 / r.k->G;
+    const unsigned need = (r.cap + ng - 1) / ng;
+    const unsigned resident = (unsigned)d.sm_count * (unsigned)std::max(1, r.k->min_blocks);
+    CK(r.k->launch(p, std::min(need, resident), smem, s.stream));
+    stats_.launches += 1;
+  }
+  CK(cudaEventRecord(s.ev_k2, s.stream));
+  if (download && P.n_pairs) {
+    const size_t nbytes = P.total_bytes - P.off_out;
+    CK(cudaMemcpyAsync(s.h_out, s.d_buf + P.off_out, nbytes, cudaMemcpyDeviceToHost, s.stream));
+    stats_.d2h += nbytes;
+  }
+  CK(cudaEventRecord(s.ev_done, s.stream));
+  return FCS_PHMM_OK;
+}
+
+// Wait for the slot's chunk and scatter its results into the caller's arrays.
+int Engine::retire_slot(Device& d, Slot& s) {
+  (void)d;
+  if (!s.busy) return FCS_PHMM_OK;
+  s.busy = false;
+  CK(cudaEventSynchronize(s.ev_done));
+  const ChunkPlan& P = s.plan;
+  float ms_all = 0.f, ms_main = 0.f;
+  CK(cudaEventElapsedTime(&ms_all, s.ev_k0, s.ev_k2));
+  CK(cudaEventElapsedTime(&ms_main, s.ev_k0, s.ev_k1));
+  const double* out = reinterpret_cast<const double*>(s.h_out);
+  const uint8_t* used = s.h_out + (P.off_used - P.off_out);
+  const float* raw = reinterpret_cast<const float*>(s.h_out + (P.off_raw - P.off_out));
+  uint64_t n64 = 0;
+  const Input& in = *s.input;
+  for (size_t k = 0; k < P.regions.size(); ++k) {
+    const int64_t g = P.regions[k];
+    int32_t nr = 0, nh = 0;
+    in.shape(g, nr, nh);
+    const size_t n = (size_t)nr * (size_t)nh;
+    if (!n) continue;
+    const uint64_t o = P.reg_out0[k];
+    std::memcpy(in.out(g), out + o, n * sizeof(double));
+    if (uint8_t* u = in.used(g)) std::memcpy(u, used + o, n);
+    if (keep_raw_)
+      if (float* r = in.raw(g)) std::memcpy(r, raw + o, n * sizeof(float));
+  }
+  for (uint64_t i = 0; i < P.n_pairs; ++i) n64 += used[i];
+  stats_.pairs += P.n_pairs;
+  stats_.cells += P.cells;
+  stats_.fp64_pairs += n64;
+  stats_.chunks += 1;
+  {
+    std::lock_guard<std::mutex> lk(stats_.mu);
+    stats_.kernel_ms += ms_all;
+    stats_.main_ms += ms_main;
+  }
+  return FCS_PHMM_OK;
+}
+
+int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& regions) {
+  std::lock_guard<std::mutex> lk(d.mu);
+  CK(cudaSetDevice(d.ordinal));
+  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 1280);
+  size_t next = 0, slot_i = 0;
+  int rc = FCS_PHMM_OK;
+  while (next < regions.size() && rc == FCS_PHMM_OK) {
+    Slot& s = d.slots[slot_i % d.slots.size()];
+    ++slot_i;
+    rc = retire_slot(d, s);
+    if (rc != FCS_PHMM_OK) break;
+    Planner pl{in, s, use_double_, keep_raw_, max_chunk_cells_, hs_cols};
+    rc = pl.run(regions, next, next);
+    if (rc != FCS_PHMM_OK) break;
+    if (s.plan.n_pairs == 0) continue;
+    rc = ensure_buffers(s, s.plan.in_bytes, s.plan.total_bytes - s.plan.off_out, s.plan.total_bytes);
+    if (rc != FCS_PHMM_OK) break;
+    rc = pack_chunk(s, in);
+    if (rc != FCS_PHMM_OK) break;
+    s.input = &in;
+    rc = launch_chunk(d, s, true, true);
+    if (rc != FCS_PHMM_OK) { cudaStreamSynchronize(s.stream); break; }
+    s.busy = true;
+  }
+  const std::string saved = rc != FCS_PHMM_OK ? std::string(last_error()) : std::string();
+  for (Slot& s : d.slots) {
+    int r2 = retire_slot(d, s);
+    if (rc == FCS_PHMM_OK && r2 != FCS_PHMM_OK) rc = r2;
+  }
+  if (!saved.empty()) set_error(rc, saved);
+  return rc;
+}
+
+int Engine::compute(const Input& in) {
+  const int64_t n = in.n_regions();
+  if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
+  if (n == 0) return FCS_PHMM_OK;
+  const size_t D = devs_.size();
+  if (D == 1) {
+    std::vector<int64_t> regs((size_t)n);
+    std::iota(regs.begin(), regs.end(), (int64_t)0);
+    return run_device(*devs_[0], in, regs);
+  }
+  // longest-processing-time-first partition of regions over the devices by DP cells
+  std::vector<std::pair<uint64_t, int64_t>> cost((size_t)n);
+  for (int64_t g = 0; g < n; ++g) {
+    int32_t nr = 0, nh = 0;
+    in.shape(g, nr, nh);
+    uint64_t sr = 0, sh = 0;
+    for (int32_t i = 0; i < nr; ++i) sr += (uint64_t)std::max(0, in.read(g, i).len);
+    for (int32_t j = 0; j < nh; ++j) sh += (uint64_t)std::max(0, in.hap(g, j).len);
+    cost[(size_t)g] = {sr * sh, g};
+  }
+  std::sort(cost.begin(), cost.end(), [](const auto& a, const auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+  std::vector<std::vector<int64_t>> part(D);
+  std::vector<uint64_t> load(D, 0);
+  for (const auto& c : cost) {
+    size_t best = 0;
+    for (size_t d = 1; d < D; ++d)
+      if (load[d] < load[best]) best = d;
+    part[best].push_back(c.second);
+    load[best] += c.first;
+  }
+  for (auto& p : part) std::sort(p.begin(), p.end());
+  std::vector<int> rcs(D, FCS_PHMM_OK);
+  std::vector<std::string> errs(D);
+  std::vector<std::thread> th;
+  for (size_t d = 0; d < D; ++d) {
+    th.emplace_back([&, d] {
+      rcs[d] = run_device(*devs_[d], in, part[d]);
+      if (rcs[d] != FCS_PHMM_OK) errs[d] = last_error();
+    });
+  }
+  for (auto& t : th) t.join();
+  for (size_t d = 0; d < D; ++d)
+    if (rcs[d] != FCS_PHMM_OK) return set_error(rcs[d], errs[d]);
+  return FCS_PHMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+int Engine::submit(std::unique_ptr<Input> in, std::shared_ptr<void> keepalive, fcs_phmm_ticket* t) {
+  std::unique_ptr<Pending> p(new Pending());
+  Pending* raw = p.get();
+  std::shared_ptr<Input> sin(in.release());
+  raw->th = std::thread([this, raw, sin, keepalive] {
+    raw->rc = compute(*sin);
+    if (raw->rc != FCS_PHMM_OK) raw->err = last_error();
+  });
+  std::lock_guard<std::mutex> lk(tickets_mu_);
+  *t = next_ticket_++;
+  tickets_[*t] = std::move(p);
+  return FCS_PHMM_OK;
+}
+
+int Engine::wait(fcs_phmm_ticket t) {
+  std::unique_ptr<Pending> p;
+  {
+    std::lock_guard<std::mutex> lk(tickets_mu_);
+    auto it = tickets_.find(t);
+    if (it == tickets_.end()) return set_error(FCS_PHMM_ETICKET, "unknown or already-waited ticket");
+    p = std::move(it->second);
+    tickets_.erase(it);
+  }
+  if (p->th.joinable()) p->th.join();
+  if (p->rc != FCS_PHMM_OK) return set_error(p->rc, p->err);
+  return FCS_PHMM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// device-resident batches
+namespace {
+class FlatInput : public Input {
+ public:
+  FlatInput(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw) : b_(b), out_(out), used_(used), raw_(raw) {}
+  int64_t n_regions() const override { return b_.n_regions; }
+  void shape(int64_t g, int32_t& nr, int32_t& nh) const override { nr = b_.reg_nreads[g]; nh = b_.reg_nhaps[g]; }
+  InRead read(int64_t g, int32_t i) const override {
+    const int64_t r = (int64_t)b_.reg_read0[g] + i;
+    const int64_t o = b_.rd_off[r];
+    return InRead{b_.read_bases + o, b_.read_q + o, b_.read_i + o, b_.read_d + o, b_.read_c + o, b_.rd_len[r]};
+  }
+  InHap hap(int64_t g, int32_t j) const override {
+    const int64_t h = (int64_t)b_.reg_hap0[g] + j;
+    return InHap{b_.hap_bases + b_.hp_off[h], b_.hp_len[h]};
+  }
+  double* out(int64_t g) const override { return out_ ? out_ + b_.reg_out0[g] : nullptr; }
+  uint8_t* used(int64_t g) const override { return used_ ? used_ + b_.reg_out0[g] : nullptr; }
+  float* raw(int64_t g) const override { return raw_ ? raw_ + b_.reg_out0[g] : nullptr; }
+
+ private:
+  fcs_phmm_flat_batch b_;
+  double* out_;
+  uint8_t* used_;
+  float* raw_;
+};
+}  // namespace
+
+std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw) {
+  return std::unique_ptr<Input>(new FlatInput(b, out, used, raw));
+}
+
+int Engine::batch_create(const fcs_phmm_flat_batch* fb, int device_index, Batch** out) {
+  *out = nullptr;
+  if (!fb) return set_error(FCS_PHMM_EINVAL, "null batch");
+  if (device_index < 0 || device_index >= (int)devs_.size()) return set_error(FCS_PHMM_EINVAL, "device index out of range");
+  Device& d = *devs_[device_index];
+  std::lock_guard<std::mutex> lk(d.mu);
+  CK(cudaSetDevice(d.ordinal));
+  std::unique_ptr<Batch> b(new Batch());
+  b->device_index = device_index;
+  // planning needs non-null out pointers only as a validity check; use a dummy base
+  static double dummy_out;
+  b->input.reset(new FlatInput(*fb, &dummy_out, nullptr, nullptr));
+  Slot& s = b->slot;
+  CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&s.ev_k0));
+  CK(cudaEventCreate(&s.ev_k1));
+  CK(cudaEventCreate(&s.ev_k2));
+  CK(cudaEventCreate(&s.ev_done));
+  std::vector<int64_t> regs((size_t)fb->n_regions);
+  std::iota(regs.begin(), regs.end(), (int64_t)0);
+  size_t next = 0;
+  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 1280);
+  Planner pl{*b->input, s, use_double_, keep_raw_, INT64_MAX, hs_cols};
+  int rc = pl.run(regs, 0, next);
+  if (rc == FCS_PHMM_OK && next != regs.size())
+    rc = set_error(FCS_PHMM_EUNSUPPORTED, "batch too large for one resident chunk (2^31 pairs / 2 GiB of reads+haplotypes)");
+  if (rc == FCS_PHMM_OK) rc = ensure_buffers(s, s.plan.in_bytes, s.plan.total_bytes - s.plan.off_out, s.plan.total_bytes);
+  if (rc == FCS_PHMM_OK) rc = pack_chunk(s, *b->input);
+  if (rc == FCS_PHMM_OK && s.plan.in_bytes) {
+    cudaError_t e = cudaMemcpyAsync(s.d_buf, s.h_in, s.plan.in_bytes, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess) rc = set_error(FCS_PHMM_ECUDA, std::string("batch upload: ") + cudaGetErrorString(e));
+  }
+  if (rc != FCS_PHMM_OK) {
+    const std::string saved = last_error();
+    free_slot(s);
+    return set_error(rc, saved);
+  }
+  for (size_t k = 0; k < s.plan.regions.size(); ++k) {
+    const int64_t g = s.plan.regions[k];
+    b->flat_out0.push_back(fb->reg_out0[g]);
+    b->reg_pairs.push_back((uint64_t)fb->reg_nreads[g] * (uint64_t)fb->reg_nhaps[g]);
+  }
+  b->input.reset();  // the caller's arrays are not needed any more
+  *out = b.release();
+  return FCS_PHMM_OK;
+}
+
+int Engine::batch_run(Batch* b, bool timed, float* total_ms, float* main_ms) {
+  if (!b) return set_error(FCS_PHMM_EINVAL, "null batch");
+  Device& d = *devs_[b->device_index];
+  std::lock_guard<std::mutex> lk(d.mu);
+  CK(cudaSetDevice(d.ordinal));
+  int rc = launch_chunk(d, b->slot, false, false);
+  if (rc != FCS_PHMM_OK) return rc;
+  if (timed) {
+    CK(cudaEventSynchronize(b->slot.ev_done));
+    float a = 0.f, m = 0.f;
+    CK(cudaEventElapsedTime(&a, b->slot.ev_k0, b->slot.ev_k2));
+    CK(cudaEventElapsedTime(&m, b->slot.ev_k0, b->slot.ev_k1));
+    if (total_ms) *total_ms = a;
+    if (main_ms) *main_ms = m;
+  }
+  return FCS_PHMM_OK;
+}
+
+int Engine::batch_sync(Batch* b) {
+  if (!b) return set_error(FCS_PHMM_EINVAL, "null batch");
+  CK(cudaSetDevice(devs_[b->device_index]->ordinal));
+  CK(cudaStreamSynchronize(b->slot.stream));
+  return FCS_PHMM_OK;
+}
+
+int Engine::batch_download(Batch* b, double* out, uint8_t* used, float* raw) {
+  if (!b) return set_error(FCS_PHMM_EINVAL, "null batch");
+  Device& d = *devs_[b->device_index];
+  std::lock_guard<std::mutex> lk(d.mu);
+  CK(cudaSetDevice(d.ordinal));
+  Slot& s = b->slot;
+  const ChunkPlan& P = s.plan;
+  if (!P.n_pairs) return FCS_PHMM_OK;
+  CK(cudaMemcpyAsync(s.h_out, s.d_buf + P.off_out, P.total_bytes - P.off_out, cudaMemcpyDeviceToHost, s.stream));
+  CK(cudaStreamSynchronize(s.stream));
+  const double* ho = reinterpret_cast<const double*>(s.h_out);
+  const uint8_t* hu = s.h_out + (P.off_used - P.off_out);
+  const float* hr = reinterpret_cast<const float*>(s.h_out + (P.off_raw - P.off_out));
+  if (raw && !keep_raw_) return set_error(FCS_PHMM_EINVAL, "raw_f32 requested but the handle was created without keep_raw_f32");
+  for (size_t k = 0; k < P.regions.size(); ++k) {
+    const uint64_t n = b->reg_pairs[k], o = P.reg_out0[k];
+    const int64_t f = b->flat_out0[k];
+    if (!n) continue;
+    if (out) std::memcpy(out + f, ho + o, n * sizeof(double));
+    if (used) std::memcpy(used + f, hu + o, n);
+    if (raw) std::memcpy(raw + f, hr + o, n * sizeof(float));
+  }
+  return FCS_PHMM_OK;
+}
+
+void Engine::batch_destroy(Batch* b) {
+  if (!b) return;
+  cudaSetDevice(devs_[b->device_index]->ordinal);
+  free_slot(b->slot);
+  delete b;
+}
+
+int Engine::get_stats(fcs_phmm_stats* s) {
+  if (!s) return set_error(FCS_PHMM_EINVAL, "null stats");
+  s->pairs = stats_.pairs;
+  s->cells = stats_.cells;
+  s->fp64_pairs = stats_.fp64_pairs;
+  s->kernel_launches = stats_.launches;
+  s->h2d_bytes = stats_.h2d;
+  s->d2h_bytes = stats_.d2h;
+  s->chunks = stats_.chunks;
+  std::lock_guard<std::mutex> lk(stats_.mu);
+  s->kernel_ms = stats_.kernel_ms;
+  s->main_kernel_ms = stats_.main_ms;
+  return FCS_PHMM_OK;
+}
+
+void Engine::reset_stats() {
+  stats_.pairs = 0; stats_.cells = 0; stats_.fp64_pairs = 0; stats_.launches = 0;
+  stats_.h2d = 0; stats_.d2h = 0; stats_.chunks = 0;
+  std::lock_guard<std::mutex> lk(stats_.mu);
+  stats_.kernel_ms = 0;
+  stats_.main_ms = 0;
+}
+
+}  // namespace fcsphmm

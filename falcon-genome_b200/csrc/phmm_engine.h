@@ -1,0 +1,159 @@
+// phmm_engine.h — host library behind the C ABI: packer (batcher), per-device chunk
+// pipeline and multi-GPU dispatcher.  See include/fcs_pairhmm.h for the contract.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fcs_pairhmm.h"
+#include "phmm_registry.h"
+#include "phmm_types.h"
+
+namespace fcsphmm {
+
+int set_error(int code, const std::string& msg);
+const char* last_error();
+
+struct InRead {
+  const uint8_t *b, *q, *i, *d, *c;
+  int32_t len;
+};
+struct InHap {
+  const uint8_t* b;
+  int32_t len;
+};
+
+// Uniform view over the two input forms (array of region structs / flat batch).
+class Input {
+ public:
+  virtual ~Input() {}
+  virtual int64_t n_regions() const = 0;
+  virtual void shape(int64_t g, int32_t& nr, int32_t& nh) const = 0;
+  virtual InRead read(int64_t g, int32_t i) const = 0;
+  virtual InHap hap(int64_t g, int32_t j) const = 0;
+  virtual double* out(int64_t g) const = 0;
+  virtual uint8_t* used(int64_t g) const = 0;
+  virtual float* raw(int64_t g) const = 0;
+};
+
+struct F32Range {
+  const KernelEntry* k;
+  uint32_t task0, n_tasks, hs_cap, hap_stage;
+};
+struct F64Range {
+  const KernelEntry* k;
+  uint32_t cls, cap, hs_cap, hap_stage;
+};
+
+// Host-side description of one packed chunk (what a slot currently holds).
+struct ChunkPlan {
+  std::vector<int64_t> regions;      // indices into the Input
+  std::vector<uint64_t> reg_out0;    // pair offset of each region inside the chunk
+  uint64_t n_reads = 0, n_haps = 0, n_pairs = 0, cells = 0;
+  size_t off_reads = 0, off_haps = 0, off_rmeta = 0, off_hmeta = 0, off_tasks = 0, off_rbase = 0, off_rcount = 0;
+  size_t off_rerun = 0, in_bytes = 0;  // input part = [0, in_bytes)
+  size_t off_out = 0, off_used = 0, off_raw = 0, total_bytes = 0;
+  size_t n_tasks = 0;
+  std::vector<F32Range> f32;
+  std::vector<F64Range> f64;
+  bool force_double = false;
+  int launches() const;
+};
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_done = nullptr;
+  uint8_t* h_in = nullptr;
+  size_t h_in_cap = 0;
+  uint8_t* h_out = nullptr;
+  size_t h_out_cap = 0;
+  uint8_t* d_buf = nullptr;
+  size_t d_cap = 0;
+  bool busy = false;
+  ChunkPlan plan;
+  const Input* input = nullptr;
+  // packer scratch (reused)
+  std::vector<std::vector<Task>> class_tasks;
+  std::vector<uint32_t> order;
+};
+
+struct Device {
+  int ordinal = 0;
+  int sm_count = 0;
+  void* d_ph2pr_f = nullptr;
+  void* d_mm_f = nullptr;
+  void* d_ph2pr_d = nullptr;
+  void* d_mm_d = nullptr;
+  std::vector<Slot> slots;
+  std::mutex mu;  // one call at a time drives a device's slots
+};
+
+struct Stats {
+  std::atomic<uint64_t> pairs{0}, cells{0}, fp64_pairs{0}, launches{0}, h2d{0}, d2h{0}, chunks{0};
+  std::mutex mu;
+  double kernel_ms = 0, main_ms = 0;
+};
+
+struct Batch;  // device-resident batch
+
+class Engine {
+ public:
+  static int create(const fcs_phmm_config* cfg, Engine** out);
+  ~Engine();
+  int compute(const Input& in);
+  int submit(std::unique_ptr<Input> in, std::shared_ptr<void> keepalive, fcs_phmm_ticket* t);
+  int wait(fcs_phmm_ticket t);
+  int batch_create(const fcs_phmm_flat_batch* b, int device_index, Batch** out);
+  int batch_run(Batch* b, bool timed, float* total_ms, float* main_ms);
+  int batch_sync(Batch* b);
+  int batch_download(Batch* b, double* out, uint8_t* used, float* raw);
+  void batch_destroy(Batch* b);
+  int get_stats(fcs_phmm_stats* s);
+  void reset_stats();
+  int device_count() const { return (int)devs_.size(); }
+
+ private:
+  Engine() {}
+  int init(const fcs_phmm_config* cfg);
+  int run_device(Device& d, const Input& in, const std::vector<int64_t>& regions);
+  int pack_chunk(Slot& s, const Input& in);
+  int launch_chunk(Device& d, Slot& s, bool upload, bool download);
+  int retire_slot(Device& d, Slot& s);
+  int ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t dev_bytes);
+  void fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) const;
+
+  std::vector<std::unique_ptr<Device>> devs_;
+  bool use_double_ = false;
+  bool keep_raw_ = false;
+  int pack_threads_ = 0;
+  int64_t max_chunk_cells_ = 0;
+  Stats stats_;
+  std::mutex tickets_mu_;
+  struct Pending {
+    std::thread th;
+    int rc = 0;
+    std::string err;
+  };
+  std::map<fcs_phmm_ticket, std::unique_ptr<Pending>> tickets_;
+  fcs_phmm_ticket next_ticket_ = 1;
+  friend struct Batch;
+};
+
+struct Batch {
+  int device_index = 0;
+  Slot slot;  // owns the buffers; plan describes the single chunk
+  std::unique_ptr<Input> input;
+  std::vector<int64_t> flat_out0;   // caller's reg_out0 per planned region
+  std::vector<uint64_t> reg_pairs;  // pairs per planned region
+};
+
+std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw);
+
+}  // namespace fcsphmm

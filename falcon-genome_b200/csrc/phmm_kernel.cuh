@@ -1,0 +1,389 @@
+// phmm_kernel.cuh — sm_100a PairHMM forward kernels (FP32 wavefront + FP64 rerun).
+//
+// Replaces (behind the C ABI in include/fcs_pairhmm.h) the native computeLikelihoodsNative
+// loop that the GATK JVMs spawned by /root/reference/src/workers/HTCWorker.cpp:48-113 and
+// src/workers/Mutect2Worker.cpp:109-192 run; semantics per SURVEY.md Appendix A.
+//
+// Design (B200-first, not a translation of the AVX anti-diagonal code):
+//  * One warp per CTA.  The warp is cut into 32/G lane groups; a group of G lanes owns ONE
+//    read, each lane a register tile of R consecutive read rows (G*R >= len+1).  All groups
+//    of the warp stream the SAME haplotypes, so one shared-memory haplotype stream feeds
+//    the whole warp.
+//  * Anti-diagonal wavefront across the G lanes: at step t lane l works on haplotype column
+//    t-l.  Only the bottom row of a lane's tile crosses to the next lane: three
+//    __shfl_up_sync per step (M, X, Y), amortised over R cells.
+//  * Per-row transition terms (pMM, pGM, pMX, pXX, pMY) live in registers for the whole
+//    task.  The per-cell prior (match ? 1-e : e/3) is NOT a compare+select: it is read
+//    from a shared-memory table  prior[symbol][lane][row]  with LDS.128 (4 rows per
+//    instruction), indexed by the haplotype symbol of the lane's current column.
+//    The table lane stride is an odd multiple of 16 B and the symbol pitch a multiple of
+//    128 B, so every quarter-warp phase is bank-conflict free whatever symbols the lanes see.
+//  * No branch, predicate or boundary select in the inner loop.  Boundaries are data:
+//      - rows above the read ("padding rows", tile top) carry constants that reproduce the
+//        row-0 boundary exactly: M = X = 0, Y = K/Lh;
+//      - columns outside the haplotype are the PAD symbol whose prior is 0, which makes
+//        M and X exactly 0 there, so the running sum of the last row is unaffected.
+//  * Reads, quals and haplotypes arrive in shared memory through cp.async.bulk (TMA bulk
+//    copy, UBLKCP in SASS) completing on an mbarrier; ph2pr comes from a shared-memory LUT.
+//  * Arithmetic is spelled with __fmul_rn/__fmaf_rn/__fadd_rn in the statement order of the
+//    oracle's float twin, so the raw FP32 sums (and therefore the FP32->FP64 fallback
+//    decisions) are bit-identical to it; same for the FP64 kernel vs the double oracle.
+//
+// Roofline: 8 FMA-pipe instructions per cell (4 FFMA + 4 FMUL); per step of R cells the
+// overhead is 3 SHFL + 1 LDS.U16 + ceil(R/4) LDS.128 + 2 FADD + address/loop ~ 2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "phmm_types.h"
+
+namespace fcsphmm {
+
+// ----------------------------------------------------------------------------------------
+// arithmetic with pinned rounding and no compiler contraction
+template <typename T>
+struct Ar;
+template <>
+struct Ar<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float K() { return 0x1p120f; }
+};
+template <>
+struct Ar<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double K() { return 0x1p1020; }
+};
+
+// ----------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (cp.async.bulk) helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ASCII base -> symbol class.  Reads: anything outside ACGTN gets 7 (matches only an N hap).
+__device__ __forceinline__ int base_code(uint32_t b) {
+  int c = 7;
+  c = (b == 'A') ? 0 : c;
+  c = (b == 'C') ? 1 : c;
+  c = (b == 'G') ? 2 : c;
+  c = (b == 'T') ? 3 : c;
+  c = (b == 'N') ? kCodeN : c;
+  return c;
+}
+
+// ----------------------------------------------------------------------------------------
+// shared-memory layout of one CTA
+template <typename T, int G, int R, bool LIST>
+struct Layout {
+  static constexpr int NG = 32 / G;
+  static constexpr int ROWS = G * R;
+  static constexpr int STRIDE = tab_stride_bytes(R, (int)sizeof(T));
+  static constexpr int SYM_PITCH = 32 * STRIDE;     // bytes between symbol rows of the table
+  static constexpr int HSCALE = SYM_PITCH / 16;     // value stored in the haplotype stream per symbol
+  static constexpr int NV = (R * (int)sizeof(T) + 15) / 16;  // LDS.128 per step
+  static constexpr int VW = 16 / (int)sizeof(T);    // values per LDS.128
+  static constexpr int RSTAGE = 5 * (int)round_up16(ROWS);   // read staging bytes per group
+  static constexpr int OFF_BAR = 0;
+  static constexpr int OFF_LUT = 128;
+  static constexpr int OFF_TAB = OFF_LUT + 128 * (int)sizeof(T);
+  static constexpr int OFF_RSTAGE = OFF_TAB + kTabRows * SYM_PITCH;
+  static constexpr int OFF_DYN = OFF_RSTAGE + NG * RSTAGE;
+  static_assert(OFF_TAB % 128 == 0, "table must start on a 128-byte line");
+  // hs_cap / hap_stage_bytes are per group when LIST, per CTA otherwise
+  static constexpr size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage_bytes) {
+    return (size_t)OFF_DYN + (size_t)(LIST ? NG : 1) * (round_up16(hs_cap * 2u) + (size_t)round_up16(hap_stage_bytes));
+  }
+};
+
+// ----------------------------------------------------------------------------------------
+// the register tile of one lane and its wavefront loop
+template <typename T, int G, int R>
+struct Tile {
+  using A = Ar<T>;
+  static constexpr int STRIDE = tab_stride_bytes(R, (int)sizeof(T));
+  static constexpr int NV = (R * (int)sizeof(T) + 15) / 16;
+  static constexpr int VW = 16 / (int)sizeof(T);
+
+  T pMM[R], pGM[R], pMX[R], pXX[R], pMY[R];
+  T pYY0;             // row 0 of the tile may need pYY != pXX (boundary replica)
+  uint32_t padmask;   // bit k: row k of this lane lies above the read
+
+  // Fill constants and this lane's slice of the prior table from the staged read.
+  // rs points at the group's staged read blob (planes of Lp bytes); len == 0 => no read.
+  __device__ __forceinline__ void build(const uint8_t* rs, uint32_t len, int lig, const T* lut, const T* __restrict__ mm,
+                                        uint8_t* tab_lane) {
+    const uint32_t Lp = round_up16(len);
+    const int npad = G * R - (int)len;
+    padmask = 0;
+    pYY0 = T(1);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int pos = lig * R + k - npad;
+      T pm = T(0), px = T(0);
+      int rcode = 6;
+      if (pos >= 0) {
+        const uint32_t b = rs[pos];
+        const uint32_t q = rs[Lp + pos] & 127u, iq = rs[2 * Lp + pos] & 127u, dq = rs[3 * Lp + pos] & 127u,
+                       cq = rs[4 * Lp + pos] & 127u;
+        const T e = lut[q];
+        pm = A::sub(T(1), e);
+        px = A::div(e, T(3));
+        const uint32_t mn = min(iq, dq), mx = max(iq, dq);
+        pMM[k] = mm[((mx * (mx + 1u)) >> 1) + mn];
+        const T pc = lut[cq];
+        pGM[k] = A::sub(T(1), pc);
+        pMX[k] = lut[iq];
+        pXX[k] = pc;
+        pMY[k] = lut[dq];
+        if (k == 0) pYY0 = pc;
+        rcode = base_code(b);
+      } else {
+        pMM[k] = T(0); pGM[k] = T(0); pMX[k] = T(0); pMY[k] = T(0);
+        pXX[k] = (k == 0) ? T(0) : T(1);   // row 0: X forced to 0 whatever arrives; below: X_up is 0 anyway, pYY must be 1
+        padmask |= 1u << k;
+      }
+#pragma unroll
+      for (int h = 0; h < 5; ++h) {
+        const bool m = (h == kCodeN) || (rcode == kCodeN) || (rcode == h);
+        const T v = (pos >= 0) ? (m ? pm : px) : T(0);
+        *reinterpret_cast<T*>(tab_lane + h * (32 * STRIDE) + k * (int)sizeof(T)) = v;
+      }
+      *reinterpret_cast<T*>(tab_lane + kCodePad * (32 * STRIDE) + k * (int)sizeof(T)) = T(0);
+    }
+  }
+
+  // One haplotype.  hs_lane[t] is the symbol offset (in 16-byte units) of the column this
+  // lane sees at step t.  Returns sum over columns of (M + X) of this lane's bottom row.
+  __device__ __forceinline__ T run(const uint8_t* tab_lane, const uint16_t* hs_lane, int nsteps, T y_init) const {
+    T M[R], X[R], Y[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      M[k] = T(0);
+      X[k] = T(0);
+      Y[k] = ((padmask >> k) & 1u) ? y_init : T(0);
+    }
+    T dM = T(0), dX = T(0);
+    T dY = __shfl_up_sync(0xffffffffu, Y[R - 1], 1, G);
+    T acc = T(0);
+#pragma unroll 2
+    for (int t = 0; t < nsteps; ++t) {
+      const uint32_t hoff = hs_lane[t];
+      const uint8_t* prow = tab_lane + hoff * 16u;
+      T pr[NV * VW];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if constexpr (sizeof(T) == 4) {
+          const float4 f = *reinterpret_cast<const float4*>(prow + v * 16);
+          pr[v * 4 + 0] = f.x; pr[v * 4 + 1] = f.y; pr[v * 4 + 2] = f.z; pr[v * 4 + 3] = f.w;
+        } else {
+          const double2 f = *reinterpret_cast<const double2*>(prow + v * 16);
+          pr[v * 2 + 0] = f.x; pr[v * 2 + 1] = f.y;
+        }
+      }
+      const T uM = __shfl_up_sync(0xffffffffu, M[R - 1], 1, G);
+      const T uX = __shfl_up_sync(0xffffffffu, X[R - 1], 1, G);
+      const T uY = __shfl_up_sync(0xffffffffu, Y[R - 1], 1, G);
+      T nM[R], nX[R], nY[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const T md = k ? M[k - 1] : dM;
+        const T xd = k ? X[k - 1] : dX;
+        const T yd = k ? Y[k - 1] : dY;
+        T s = A::mul(md, pMM[k]);
+        s = A::fma(xd, pGM[k], s);
+        s = A::fma(yd, pGM[k], s);
+        nM[k] = A::mul(s, pr[k]);
+        nY[k] = A::fma(Y[k], k ? pXX[k] : pYY0, A::mul(M[k], pMY[k]));
+      }
+      nX[0] = A::fma(uX, pXX[0], A::mul(uM, pMX[0]));
+#pragma unroll
+      for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], pXX[k], A::mul(nM[k - 1], pMX[k]));
+      acc = A::add(acc, A::add(nM[R - 1], nX[R - 1]));
+      dM = uM; dX = uX; dY = uY;
+#pragma unroll
+      for (int k = 0; k < R; ++k) { M[k] = nM[k]; X[k] = nX[k]; Y[k] = nY[k]; }
+    }
+    return acc;
+  }
+};
+
+// ----------------------------------------------------------------------------------------
+// result emission
+__device__ __forceinline__ void emit_f32(const KParams& p, const ReadMeta& rm, uint32_t read, uint32_t hap, float S) {
+  const uint32_t oi = rm.out_off + (hap - rm.hap0);
+  if (p.raw_f32) p.raw_f32[oi] = S;
+  if (S < 1e-28f) {  // GKL MIN_ACCEPTED: queue the pair for the double-precision kernel
+    const uint32_t cls = rm.len_cls >> 24;
+    const uint32_t slot = atomicAdd(&p.rerun_count[cls], 1u);
+    RerunEntry e;
+    e.read = read;
+    e.hap = hap;
+    p.rerun[p.rerun_base[cls] + slot] = e;
+    p.used_fp64[oi] = 1;
+  } else {
+    // (float)log10((double)S): the correctly rounded log10f(S); K = 2^120
+    const float l = (float)log10((double)S);
+    const float k = 0x1.20fd22p+5f;  // (float)log10(2^120)
+    p.out[oi] = (double)__fsub_rn(l, k);
+    p.used_fp64[oi] = 0;
+  }
+}
+__device__ __forceinline__ void emit_f64(const KParams& p, const ReadMeta& rm, uint32_t hap, double S) {
+  const uint32_t oi = rm.out_off + (hap - rm.hap0);
+  p.out[oi] = log10(S) - 0x1.330cf3d4eda85p+8;  // log10(2^1020) as glibc rounds it (307.0505955772608)
+  p.used_fp64[oi] = 1;
+}
+
+// ----------------------------------------------------------------------------------------
+// FP32 main kernel: one task per CTA (<= 32/G reads of a region x a run of its haplotypes).
+// FP64 rerun kernel (LIST): grid-stride over the (read, hap) queue, one pair per lane group.
+template <typename T, int G, int R, bool LIST, int MINB>
+__global__ void __launch_bounds__(32, MINB) phmm_kernel(const KParams p) {
+  using L = Layout<T, G, R, LIST>;
+  using A = Ar<T>;
+  constexpr int NG = L::NG;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x;
+  const int grp = lane / G, lig = lane % G;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  T* lut = reinterpret_cast<T*>(smem + L::OFF_LUT);
+  uint8_t* tab_lane = smem + L::OFF_TAB + lane * L::STRIDE;
+  uint8_t* rstage = smem + L::OFF_RSTAGE + grp * L::RSTAGE;
+  const uint32_t hs_bytes = round_up16(p.hs_cap * 2u);
+  const uint32_t hstage_bytes = round_up16(p.hap_stage_bytes);
+  uint16_t* hs = reinterpret_cast<uint16_t*>(smem + L::OFF_DYN) + (LIST ? grp * (hs_bytes / 2u) : 0u);
+  uint8_t* hstage = smem + L::OFF_DYN + (LIST ? NG : 1) * hs_bytes + (LIST ? grp * hstage_bytes : 0u);
+  const T* __restrict__ mm = reinterpret_cast<const T*>(p.mm);
+
+  for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  uint32_t parity = 0;
+  Tile<T, G, R> tile;
+
+  if constexpr (!LIST) {
+    const Task task = p.tasks[blockIdx.x];
+    const bool active = grp < (int)task.n_reads;
+    const uint32_t read = task.read0 + (active ? grp : 0);
+    const ReadMeta rm = p.rmeta[read];
+    const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
+    const HapMeta h_first = p.hmeta[task.hap0];
+    const HapMeta h_last = p.hmeta[task.hap0 + task.n_haps - 1];
+    const uint32_t hap_bytes = (h_last.data_off16 - h_first.data_off16) * 16u + round_up16(h_last.len);
+    // ---- stage reads + haplotypes with TMA bulk copies
+    const uint32_t my_bytes = ((active && lig == 0) ? 5u * round_up16(rlen) : 0u) + (lane == 0 ? hap_bytes : 0u);
+    const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
+    if (lane == 0) mbar_expect_tx(bar, tot);
+    __syncwarp();
+    if (active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
+    if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    // ---- per-row constants + prior table
+    tile.build(rstage, rlen, lig, lut, mm, tab_lane);
+    // ---- haplotype stream: [G-1 PAD] hap0 [G-1 PAD] hap1 ... [G-1 PAD]
+    uint32_t off = 0;
+    for (uint32_t j = 0; j < task.n_haps; ++j) {
+      const HapMeta hm = p.hmeta[task.hap0 + j];
+      const uint8_t* src = hstage + (hm.data_off16 - h_first.data_off16) * 16u;
+      if (lane < G - 1) hs[off + lane] = (uint16_t)(kCodePad * L::HSCALE);
+      for (uint32_t x = lane; x < hm.len; x += 32) {
+        int c = base_code(src[x]);
+        c = (c > kCodeN) ? kCodePad : c;  // host rejects such haplotypes; never reached
+        hs[off + (G - 1) + x] = (uint16_t)(c * L::HSCALE);
+      }
+      off += (G - 1) + hm.len;
+    }
+    if (lane < G - 1) hs[off + lane] = (uint16_t)(kCodePad * L::HSCALE);
+    __syncwarp();
+    // ---- wavefront over every haplotype of the task
+    off = 0;
+    for (uint32_t j = 0; j < task.n_haps; ++j) {
+      const uint32_t Lh = p.hmeta[task.hap0 + j].len;
+      const T y_init = A::div(A::K(), (T)(int)Lh);
+      const T acc = tile.run(tab_lane, hs + off + (G - 1) - lig, (int)Lh + G - 1, y_init);
+      off += (G - 1) + Lh;
+      if (active && lig == G - 1) {
+        if constexpr (sizeof(T) == 4) emit_f32(p, rm, read, task.hap0 + j, acc);
+        else emit_f64(p, rm, task.hap0 + j, acc);
+      }
+    }
+  } else {
+    const uint32_t count = p.rerun_count[p.f64_class];
+    const RerunEntry* list = p.rerun + p.rerun_base[p.f64_class];
+    for (uint32_t base = blockIdx.x * NG; base < count; base += gridDim.x * NG) {
+      const bool active = base + grp < count;
+      RerunEntry e;
+      e.read = 0; e.hap = 0;
+      if (active) e = list[base + grp];
+      const ReadMeta rm = p.rmeta[e.read];
+      const HapMeta hm = p.hmeta[e.hap];
+      const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
+      const uint32_t Lh = active ? hm.len : 0u;
+      fence_proxy_async();  // staging was read through the generic proxy last round
+      const uint32_t my_bytes = (active && lig == 0) ? 5u * round_up16(rlen) + round_up16(Lh) : 0u;
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
+      if (lane == 0) mbar_expect_tx(bar, tot);
+      __syncwarp();
+      if (active && lig == 0) {
+        bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
+        bulk_g2s(hstage, p.haps + (size_t)hm.data_off16 * 16u, round_up16(Lh), bar);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      tile.build(rstage, rlen, lig, lut, mm, tab_lane);
+      const uint32_t Lmax = __reduce_max_sync(0xffffffffu, Lh);
+      const uint32_t total = Lmax + 2u * (G - 1);
+      for (uint32_t x = lig; x < total; x += G) {
+        int c = kCodePad;
+        if (x >= (uint32_t)(G - 1) && x < (uint32_t)(G - 1) + Lh) {
+          c = base_code(hstage[x - (G - 1)]);
+          c = (c > kCodeN) ? kCodePad : c;
+        }
+        hs[x] = (uint16_t)(c * L::HSCALE);
+      }
+      __syncwarp();
+      const T y_init = A::div(A::K(), (T)(int)(Lh ? Lh : 1u));
+      const T acc = tile.run(tab_lane, hs + (G - 1) - lig, (int)Lmax + G - 1, y_init);
+      if (active && lig == G - 1) {
+        if constexpr (sizeof(T) == 4) emit_f32(p, rm, e.read, e.hap, acc);
+        else emit_f64(p, rm, e.hap, acc);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace fcsphmm

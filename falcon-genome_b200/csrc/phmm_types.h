@@ -1,0 +1,86 @@
+// phmm_types.h — device-visible data layout shared by the packer (host) and the kernels.
+//
+// HBM layout of one packed chunk (every section 16-byte aligned so that one
+// cp.async.bulk moves a read set or a haplotype set into shared memory):
+//
+//   reads   : per read  [bases | base_q | ins_q | del_q | gcp], each plane padded to
+//             Lp = round_up(len, 16) bytes  -> 5*Lp bytes per read, reads of a task adjacent
+//   haps    : per hap   bases padded to round_up(len, 16)
+//   rmeta[] : ReadMeta per read,  hmeta[] : HapMeta per hap,  tasks[] : Task per CTA
+//   out[]   : double per pair, used[] : u8 per pair, raw[] : float per pair (optional)
+//   rerun[] : (read, hap) pairs queued for the double-precision kernel, one segment per
+//             FP64 kernel class, filled by the FP32 kernel with atomics
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PHMM_HD __host__ __device__
+#else
+#define PHMM_HD
+#endif
+
+namespace fcsphmm {
+
+constexpr int kTabRows = 6;  // haplotype symbol classes: A C G T N PAD
+constexpr int kCodeN = 4;
+constexpr int kCodePad = 5;
+constexpr int kMaxF64Classes = 40;
+
+struct ReadMeta {
+  uint32_t data_off16;  // offset of the read blob in `reads`, in 16-byte units
+  uint32_t len_cls;     // len | (fp64 class id << 24)
+  uint32_t out_off;     // index in out[] of (this read, first hap of its region)
+  uint32_t hap0;        // first hap (chunk-wide index) of its region
+};
+
+struct HapMeta {
+  uint32_t data_off16;
+  uint32_t len;
+};
+
+// One CTA (one warp) of the FP32 wavefront kernel: up to 32/G reads of one region
+// against a run of that region's haplotypes.
+struct Task {
+  uint32_t read0;
+  uint32_t hap0;
+  uint16_t n_reads;
+  uint16_t n_haps;
+  uint32_t reserved;
+};
+
+struct RerunEntry {
+  uint32_t read;
+  uint32_t hap;
+};
+
+struct KParams {
+  const uint8_t* reads;
+  const uint8_t* haps;
+  const ReadMeta* rmeta;
+  const HapMeta* hmeta;
+  const Task* tasks;       // FP32 main kernels: tasks of this class
+  uint32_t n_tasks;
+  const void* ph2pr;       // T[128]
+  const void* mm;          // T[8256], index ((max*(max+1))>>1)+min
+  double* out;
+  uint8_t* used_fp64;
+  float* raw_f32;          // may be null
+  RerunEntry* rerun;       // base of all segments
+  uint32_t* rerun_count;   // [kMaxF64Classes]
+  const uint32_t* rerun_base;  // [kMaxF64Classes] segment start (entries)
+  uint32_t f64_class;      // FP64 kernels: which segment this launch drains
+  uint32_t hs_cap;         // u16 entries of haplotype stream in shared memory
+  uint32_t hap_stage_bytes;  // bytes of raw haplotype staging in shared memory
+};
+
+PHMM_HD inline constexpr uint32_t round_up16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// Table lane stride in bytes: smallest odd multiple of 16 that holds R values of size esz.
+// Odd => the eight lanes of a quarter-warp LDS.128 phase hit eight distinct 16-byte bank groups.
+PHMM_HD inline constexpr int tab_stride_bytes(int R, int esz) {
+  int n16 = (R * esz + 15) / 16;
+  if ((n16 & 1) == 0) n16 += 1;
+  return n16 * 16;
+}
+
+}  // namespace fcsphmm

@@ -1,0 +1,194 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): |dlog10 L| <= 1e-4 per pair vs the double-precision oracle,
+identical FP32->FP64 fallback decisions, identical per-read best haplotype.  Stronger, by
+construction of the kernels: raw FP32 sums bit-identical to the oracle's float twin and FP64
+results equal to the double oracle to 1e-12.
+"""
+import numpy as np
+import pytest
+
+from falcon_genome_b200 import FlatBatch, PairHMM, Region, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # |delta log10 L| per pair, north_star
+
+
+def check_against_oracle(oracle, b, out, used, raw=None, simd=True):
+    if simd:
+        o_ref, u_ref, r_ref, _ = oracle.batch_simd(b)  # bit-identical to the scalar twin (tests/test_oracle.py)
+        dbl = None
+    else:
+        o_ref, u_ref, r_ref, dbl = oracle.batch_scalar(b)
+    assert np.array_equal(used, u_ref), f"fallback decisions differ on {(used != u_ref).sum()} of {len(used)} pairs"
+    if raw is not None:
+        assert np.array_equal(raw.view(np.uint32), r_ref.view(np.uint32)), "raw FP32 sums are not bit-identical to the float twin"
+    fin = np.isfinite(o_ref)
+    assert np.array_equal(fin, np.isfinite(out))
+    err = np.abs(out[fin] - o_ref[fin])
+    assert err.max() <= TOL, f"max |dlog10L| = {err.max()}"
+    # FP64 path: same operation order as the oracle -> agreement far below the tolerance
+    if used.any():
+        assert np.abs(out[used == 1] - o_ref[used == 1])[np.isfinite(o_ref[used == 1])].max() <= 1e-9
+    if dbl is not None:
+        assert np.abs(out[fin] - dbl[fin]).max() <= TOL  # vs the double-precision oracle for EVERY pair
+    # per-read best haplotype (ties -> lowest h)
+    for g in range(b.n_regions):
+        nr, nh, o0 = int(b.reg_nreads[g]), int(b.reg_nhaps[g]), int(b.reg_out0[g])
+        if nr and nh:
+            a = out[o0:o0 + nr * nh].reshape(nr, nh)
+            r = o_ref[o0:o0 + nr * nh].reshape(nr, nh)
+            assert np.array_equal(a.argmax(1), r.argmax(1))
+    return float(err.max())
+
+
+def test_kat_single_cell(hmm):
+    rd = (b"A", bytes([30]), bytes([45]), bytes([45]), bytes([10]))
+    m = hmm.compute_likelihoods([rd], [b"A", b"C", b"AAAAA", b"N"])
+    assert abs(m[0, 0] - np.log10(0.999 * 0.9)) < 1e-6
+    assert abs(m[0, 1] - np.log10(0.001 / 3 * 0.9)) < 1e-6
+    assert abs(m[0, 2] - np.log10(0.999 * 0.9)) < 1e-6
+    assert abs(m[0, 3] - np.log10(0.999 * 0.9)) < 1e-6
+
+
+def test_tiny_mixed_all_entry_points(hmm, oracle):
+    b = synth.tiny_mixed()
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+    out2, used2 = hmm.compute_regions(b)
+    assert np.array_equal(out, out2) and np.array_equal(used, used2)
+    rb = hmm.resident(b)
+    rb.run()
+    out3, used3, raw3 = rb.download(want_raw=True)
+    rb.close()
+    assert np.array_equal(out, out3) and np.array_equal(used, used3) and np.array_equal(raw, raw3)
+
+
+@pytest.mark.parametrize("seed", [7, 8, 9, 10])
+def test_ragged_seeds(hmm, oracle, seed):
+    b = synth.tiny_mixed(seed=seed, n_regions=12)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+
+
+def test_config1_golden_sample(hmm, oracle):
+    b = synth.config1_golden(n_regions=24)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw)
+
+
+def test_config2_sample(hmm, oracle):
+    b = synth.config2_uniform(n_regions=6)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw)
+    b = synth.config2_uniform(n_regions=3, random_quals=True)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw)
+
+
+def test_config3_sample(hmm, oracle):
+    b = synth.config3_wgs(n_regions=30)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw)
+
+
+def test_config4_sample(hmm, oracle):
+    b = synth.config4_mutect2(n_regions=1)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw)
+
+
+def test_config5_underflow_fallback(hmm, oracle):
+    b = synth.config5_underflow(n_regions=3)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw)
+    assert used.mean() > 0.5, "the underflow stress config must mostly take the FP64 path"
+
+
+def test_force_double_matches_double_oracle(oracle):
+    b = synth.tiny_mixed(seed=3, n_regions=8)
+    with PairHMM(use_double=True) as h:
+        out, used = h.compute_flat(b)
+    assert used.all()
+    _, _, _, dbl = oracle.batch_scalar(b)
+    assert np.abs(out - dbl).max() <= 1e-9
+
+
+def test_every_read_length_class(hmm, oracle):
+    """Read lengths sweep the (G, R) kernel classes, including exact tile fits G*R-1."""
+    rng = np.random.default_rng(5)
+    regs = []
+    lens = [1, 2, 3, 15, 16, 23, 24, 47, 48, 63, 64, 95, 96, 103, 104, 127, 128, 151, 152, 159, 160, 191, 192, 207, 208,
+            255, 256, 300, 383, 384, 415, 416, 500, 640, 767]
+    hap = bytes(rng.choice(list(b"ACGT"), 333).astype(np.uint8))
+    for L in lens:
+        s = int(rng.integers(0, max(1, 333 - L)))
+        bases = (hap + hap + hap)[s:s + L]
+        q = bytes(rng.integers(6, 42, L).astype(np.uint8))
+        i = bytes(rng.integers(20, 46, L).astype(np.uint8))
+        d = bytes(rng.integers(20, 46, L).astype(np.uint8))
+        c = bytes(rng.integers(8, 12, L).astype(np.uint8))
+        regs.append(Region([(bases, q, i, d, c)], [hap, hap[:100], hap[50:]]))
+    b = FlatBatch.from_regions(regs)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+
+
+def test_batching_invariance(hmm):
+    """Shuffling regions, splitting a call, or shrinking chunks changes no output bit."""
+    b = synth.config1_golden(n_regions=16, seed=11)
+    out, used = hmm.compute_flat(b)
+    perm = np.random.default_rng(0).permutation(b.n_regions)
+    bp = b.select(perm)
+    outp, usedp = hmm.compute_flat(bp)
+    for k, g in enumerate(perm):
+        n = int(b.reg_nreads[g]) * int(b.reg_nhaps[g])
+        assert np.array_equal(out[b.reg_out0[g]:b.reg_out0[g] + n], outp[bp.reg_out0[k]:bp.reg_out0[k] + n])
+    with PairHMM(max_chunk_cells=2_000_000, slots_per_device=2) as h2:
+        out2, used2 = h2.compute_flat(b)
+        st = h2.stats()
+    assert st["chunks"] > 3
+    assert np.array_equal(out, out2) and np.array_equal(used, used2)
+
+
+def test_submit_wait(hmm):
+    from falcon_genome_b200 import RegionArray
+
+    b = synth.tiny_mixed(seed=21)
+    ref, _ = hmm.compute_flat(b)
+    ra = RegionArray(b)
+    t = hmm.submit(ra)
+    hmm.wait(t)
+    assert np.array_equal(ra.out, ref)
+    with pytest.raises(Exception):
+        hmm.wait(t)
+
+
+def test_errors(hmm):
+    from falcon_genome_b200 import PairHMMError
+
+    rd = (b"ACGT", bytes([30] * 4), bytes([45] * 4), bytes([45] * 4), bytes([10] * 4))
+    with pytest.raises(PairHMMError) as e:
+        hmm.compute_likelihoods([rd], [b"ACXT"])
+    assert e.value.code == -1
+    with pytest.raises(PairHMMError) as e:
+        hmm.compute_likelihoods([rd], [b""])
+    assert e.value.code == -1
+    # empty regions are fine
+    b = FlatBatch.from_regions([Region([], [b"ACGT"]), Region([rd], []), Region([rd], [b"ACGT"])])
+    out, used = hmm.compute_flat(b)
+    assert out.shape == (1,) and np.isfinite(out[0])
+
+
+def test_full_size_config2_properties(hmm):
+    """BASELINE config 2 at full size (100k pairs): size-independent properties instead of the
+    oracle — every read's best haplotype scores far above a random one, results are finite, no
+    pair needs FP64, and the run is bit-reproducible."""
+    b = synth.config2_uniform()
+    out, used = hmm.compute_flat(b)
+    assert np.isfinite(out).all() and not used.any()
+    out2, _ = hmm.compute_flat(b)
+    assert np.array_equal(out, out2)
+    m = out.reshape(100, 100, 10)
+    assert (m.max(axis=2) > -12).all() and (m <= 0).all()

@@ -50,13 +50,22 @@ static int64_t env_i64(const char* name, int64_t dflt) {
 static std::vector<const KernelEntry*> g_f32_classes, g_f64_classes;
 static std::once_flag g_cls_once;
 static void build_class_lists() {
-  for (const KernelEntry* k = kernel_table(); k->G != 0; ++k) (k->f64 ? g_f64_classes : g_f32_classes).push_back(k);
+  // class ids index the GENERAL-form entries; the uniform-GCP twin of a class has the same (G, R)
+  for (const KernelEntry* k = kernel_table(); k->G != 0; ++k)
+    if (!k->ug) (k->f64 ? g_f64_classes : g_f32_classes).push_back(k);
 }
 static int class_id(const KernelEntry* k) {
   const auto& v = k->f64 ? g_f64_classes : g_f32_classes;
   for (size_t i = 0; i < v.size(); ++i)
-    if (v[i] == k) return (int)i;
+    if (v[i]->G == k->G && v[i]->R == k->R) return (int)i;
   return -1;
+}
+// The value all gap-continuation quals of a read share (masked & 127 like the kernels), or -1.
+static int uniform_gcp(const uint8_t* c, int32_t len) {
+  const uint8_t v = c[0] & 127u;
+  uint8_t diff = 0;
+  for (int32_t i = 1; i < len; ++i) diff |= (uint8_t)((c[i] & 127u) ^ v);
+  return diff ? -1 : (int)v;
 }
 
 int ChunkPlan::launches() const {
@@ -213,11 +222,11 @@ struct Planner {
     ChunkPlan& P = s.plan;
     P = ChunkPlan();
     P.force_double = force_double;
-    s.class_tasks.resize(g_f32_classes.size());
-    for (auto& v : s.class_tasks) v.clear();
+    for (auto& b : s.buckets) { b.tasks.clear(); b.hs = 0; b.stage = 0; }
     s.order.clear();
-    std::vector<uint32_t> f32_hs(g_f32_classes.size(), 0), f32_stage(g_f32_classes.size(), 0);
     std::vector<uint32_t> f64_cap(g_f64_classes.size(), 0), f64_maxlh(g_f64_classes.size(), 0);
+    std::vector<int> gcps;
+    int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
     size_t reads_bytes = 0, haps_bytes = 0;
     std::vector<uint32_t> lens, hlens;
     size_t k = first;
@@ -233,6 +242,7 @@ struct Planner {
       }
       if (!in.out(g)) return set_error(FCS_PHMM_EINVAL, "out_log10 is null");
       lens.resize(nr);
+      gcps.resize(nr);
       hlens.resize(nh);
       uint64_t sum_r = 0, sum_h = 0;
       size_t rb = 0, hb = 0;
@@ -240,9 +250,10 @@ struct Planner {
         const InRead r = in.read(g, i);
         if (r.len <= 0 || !r.b || !r.q || !r.i || !r.d || !r.c)
           return set_error(FCS_PHMM_EINVAL, "read with non-positive length or null array");
-        if (!select_kernel(false, r.len) || !select_kernel(true, r.len))
+        if (!select_kernel(false, false, r.len) || !select_kernel(true, false, r.len))
           return set_error(FCS_PHMM_EUNSUPPORTED, "read length " + std::to_string(r.len) + " exceeds the compiled kernel classes");
         lens[i] = (uint32_t)r.len;
+        gcps[i] = uniform_gcp(r.c, r.len);
         sum_r += (uint64_t)r.len;
         rb += 5u * round_up16((uint32_t)r.len);
       }
@@ -272,10 +283,22 @@ struct Planner {
       // ---- tasks
       const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
       for (int32_t i = 0; i < nr;) {
-        const KernelEntry* kc = select_kernel(false, (int)lens[ord[i]]);
+        const KernelEntry* kc = select_kernel(false, false, (int)lens[ord[i]]);
         const int cid = class_id(kc);
         const int NG = 32 / kc->G;
         const int cnt = std::min<int32_t>(NG, nr - i);
+        int tg = gcps[ord[i]];  // uniform-GCP launch only if every read of the task shares the value
+        for (int32_t x = 1; x < cnt; ++x)
+          if (gcps[ord[i + x]] != tg) tg = -1;
+        TaskBucket* bk = nullptr;
+        for (auto& b : s.buckets)
+          if (b.cid == cid && b.gcp == tg) { bk = &b; break; }
+        if (!bk) {
+          s.buckets.emplace_back();
+          bk = &s.buckets.back();
+          bk->cid = cid;
+          bk->gcp = tg;
+        }
         for (int32_t j = 0; j < nh;) {
           uint32_t cols = 0, stage = 0;
           int32_t j1 = j;
@@ -291,9 +314,9 @@ struct Planner {
           t.n_reads = (uint16_t)cnt;
           t.n_haps = (uint16_t)(j1 - j);
           t.reserved = 0;
-          s.class_tasks[cid].push_back(t);
-          f32_hs[cid] = std::max(f32_hs[cid], cols);
-          f32_stage[cid] = std::max(f32_stage[cid], stage);
+          bk->tasks.push_back(t);
+          bk->hs = std::max(bk->hs, cols);
+          bk->stage = std::max(bk->stage, stage);
           j = j1;
         }
         i += cnt;
@@ -302,9 +325,10 @@ struct Planner {
       uint32_t maxlh = 0;
       for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
       for (int32_t i = 0; i < nr; ++i) {
-        const int c64 = class_id(select_kernel(true, (int)lens[i]));
+        const int c64 = class_id(select_kernel(true, false, (int)lens[i]));
         f64_cap[c64] += (uint32_t)nh;
         f64_maxlh[c64] = std::max(f64_maxlh[c64], maxlh);
+        chunk_gcp = (chunk_gcp == -2) ? gcps[i] : (chunk_gcp == gcps[i] ? chunk_gcp : -1);
       }
       P.regions.push_back(g);
       P.reg_out0.push_back(P.n_pairs);
@@ -324,17 +348,23 @@ struct Planner {
     P.off_hmeta = off; off = align_up(off + P.n_haps * sizeof(HapMeta), 256);
     P.off_tasks = off;
     P.n_tasks = 0;
-    for (size_t c = 0; c < s.class_tasks.size(); ++c) {
-      if (s.class_tasks[c].empty()) continue;
+    for (size_t bi = 0; bi < s.buckets.size(); ++bi) {
+      const TaskBucket& b = s.buckets[bi];
+      if (b.tasks.empty()) continue;
       F32Range r;
-      r.k = g_f32_classes[c];
+      const KernelEntry* gk = g_f32_classes[b.cid];
+      r.k = b.gcp >= 0 ? find_kernel(false, true, gk->G, gk->R) : gk;
+      if (!r.k) r.k = gk;
+      r.gcp = r.k->ug ? b.gcp : -1;
+      r.bucket = (uint32_t)bi;
       r.task0 = (uint32_t)P.n_tasks;
-      r.n_tasks = (uint32_t)s.class_tasks[c].size();
-      r.hs_cap = f32_hs[c];
-      r.hap_stage = f32_stage[c];
+      r.n_tasks = (uint32_t)b.tasks.size();
+      r.hs_cap = b.hs;
+      r.hap_stage = b.stage;
       P.f32.push_back(r);
       P.n_tasks += r.n_tasks;
     }
+    P.f64_gcp = chunk_gcp >= 0 ? chunk_gcp : -1;
     off = align_up(off + P.n_tasks * sizeof(Task), 256);
     P.off_rbase = off; off += kMaxF64Classes * sizeof(uint32_t);
     P.off_rcount = off; off += kMaxF64Classes * sizeof(uint32_t);
@@ -344,6 +374,8 @@ struct Planner {
       if (!f64_cap[c]) continue;
       F64Range r;
       r.k = g_f64_classes[c];
+      if (P.f64_gcp >= 0)
+        if (const KernelEntry* uk = find_kernel(true, true, r.k->G, r.k->R)) r.k = uk;
       r.cls = (uint32_t)c;
       r.cap = f64_cap[c];
       r.hs_cap = f64_maxlh[c] + 2u * (uint32_t)(r.k->G - 1);
@@ -422,7 +454,7 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
         std::memcpy(dst + (size_t)pl * lp, src[pl], (size_t)r.len);
         std::memset(dst + (size_t)pl * lp + r.len, 0, lp - (uint32_t)r.len);
       }
-      const int c64 = class_id(select_kernel(true, r.len));
+      const int c64 = class_id(select_kernel(true, false, r.len));
       ReadMeta& m = rmeta[ridx];
       m.data_off16 = (uint32_t)(rpos / 16);
       m.len_cls = (uint32_t)r.len | ((uint32_t)c64 << 24);
@@ -442,8 +474,7 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
     for (const F64Range& r : P.f64) rcount[r.cls] = fill[r.cls];
   Task* tasks = reinterpret_cast<Task*>(base + P.off_tasks);
   for (const F32Range& r : P.f32) {
-    const int cid = class_id(r.k);
-    std::memcpy(tasks + r.task0, s.class_tasks[cid].data(), (size_t)r.n_tasks * sizeof(Task));
+    std::memcpy(tasks + r.task0, s.buckets[r.bucket].tasks.data(), (size_t)r.n_tasks * sizeof(Task));
   }
   return FCS_PHMM_OK;
 }
@@ -468,6 +499,17 @@ void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) 
   p.f64_class = 0;
   p.hs_cap = 0;
   p.hap_stage_bytes = 0;
+  p.c_xx_f = 0.f; p.c_gm_f = 0.f; p.c_xx_d = 0.0; p.c_gm_d = 0.0;
+}
+
+// launch constants of a uniform-GCP launch, from the same tables the kernels index
+static void set_gcp_constants(KParams& p, int gcp) {
+  if (gcp < 0) return;
+  const Luts& L = luts();
+  p.c_xx_f = L.ph2pr_f[gcp & 127];
+  p.c_gm_f = 1.0f - p.c_xx_f;
+  p.c_xx_d = L.ph2pr_d[gcp & 127];
+  p.c_gm_d = 1.0 - p.c_xx_d;
 }
 
 // Enqueue one chunk on the slot's stream.  upload/download = include the H2D / D2H copies.
@@ -489,6 +531,7 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
       p.n_tasks = r.n_tasks;
       p.hs_cap = r.hs_cap;
       p.hap_stage_bytes = r.hap_stage;
+      set_gcp_constants(p, r.gcp);
       const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
       if (smem > 227 * 1024)
         return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype run does not fit in shared memory (" + std::to_string(smem) + " bytes)");
@@ -504,6 +547,7 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
     p.f64_class = r.cls;
     p.hs_cap = r.hs_cap;
     p.hap_stage_bytes = r.hap_stage;
+    set_gcp_constants(p, r.k->ug ? P.f64_gcp : -1);
     const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
     if (smem > 227 * 1024)
       return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype too long for the FP64 kernel's shared memory (" + std::to_string(smem) + " bytes)");

@@ -46,6 +46,14 @@ class Input {
 struct F32Range {
   const KernelEntry* k;
   uint32_t task0, n_tasks, hs_cap, hap_stage;
+  uint32_t bucket;  // index of the TaskBucket the tasks come from
+  int gcp;          // >= 0: uniform-GCP launch with this quality, -1: general form
+};
+// Tasks of one launch: one kernel class x one gap-continuation value (or -1 = mixed).
+struct TaskBucket {
+  int cid = 0, gcp = -1;
+  uint32_t hs = 0, stage = 0;
+  std::vector<Task> tasks;
 };
 struct F64Range {
   const KernelEntry* k;
@@ -64,6 +72,7 @@ struct ChunkPlan {
   std::vector<F32Range> f32;
   std::vector<F64Range> f64;
   bool force_double = false;
+  int f64_gcp = -1;  // >= 0: every read of the chunk shares this gap-continuation quality
   int launches() const;
 };
 
@@ -80,7 +89,7 @@ struct Slot {
   ChunkPlan plan;
   const Input* input = nullptr;
   // packer scratch (reused)
-  std::vector<std::vector<Task>> class_tasks;
+  std::vector<TaskBucket> buckets;
   std::vector<uint32_t> order;
 };
 

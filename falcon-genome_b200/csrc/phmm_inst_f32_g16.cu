@@ -1,6 +1,6 @@
-// FP32 wavefront kernels, G = 16 lanes per read.
+// FP32 wavefront kernels (general form), G = 16 lanes per read.
 #include "phmm_classes.h"
 #include "phmm_inst.cuh"
 namespace fcsphmm {
-extern const KernelEntry kEntriesF32G16[] = {PHMM_F32_G16(PHMM_ENTRY_F32){0, 0, false, nullptr, nullptr, nullptr, 0}};
+extern const KernelEntry kEntriesF32G16[] = {PHMM_F32_G16(PHMM_ENTRY_F32) PHMM_ENTRY_END};
 }

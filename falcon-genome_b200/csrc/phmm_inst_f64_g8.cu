@@ -1,6 +1,6 @@
-// FP64 rerun kernels, G = 8 lanes per read.
+// FP64 rerun kernels (general and uniform-GCP forms), G = 8 lanes per read.
 #include "phmm_classes.h"
 #include "phmm_inst.cuh"
 namespace fcsphmm {
-extern const KernelEntry kEntriesF64G8[] = {PHMM_F64_G8(PHMM_ENTRY_F64){0, 0, false, nullptr, nullptr, nullptr, 0}};
+extern const KernelEntry kEntriesF64G8[] = {PHMM_F64_G8(PHMM_ENTRY_F64) PHMM_F64_G8(PHMM_ENTRY_F64U) PHMM_ENTRY_END};
 }

@@ -129,16 +129,32 @@ struct Layout {
 
 // ----------------------------------------------------------------------------------------
 // the register tile of one lane and its wavefront loop
-template <typename T, int G, int R>
+//
+// UG ("uniform GCP"): every read of the launch has one constant gap-continuation quality
+// (GATK HaplotypeCaller / Mutect2 always pass a constant 10 [upstream, SURVEY A.6]).  Then
+// pXX = pYY = ph2pr[gcp] and pGM = 1 - pXX are launch constants that the FMAs take from the
+// constant bank instead of the register file.  The register file feeds about two 32-bit
+// operands per clock per SM sub-partition (measured, tools/ubench/fp32_issue.cu), so the
+// operand reads per cell, not the issue slots, bound this kernel: 20 reads/cell in the general
+// form, 17 with UG (and 7 instead of 8 registers per row).  Only the Y update keeps a per-row
+// multiplier (pYY[k] = 1 on the rows above the read, so their Y stays K/Lh).
+template <typename T, int G, int R, bool UG>
 struct Tile {
   using A = Ar<T>;
   static constexpr int STRIDE = tab_stride_bytes(R, (int)sizeof(T));
   static constexpr int NV = (R * (int)sizeof(T) + 15) / 16;
   static constexpr int VW = 16 / (int)sizeof(T);
+  static constexpr int RG = UG ? 1 : R;  // rows that keep their own pGM / pXX
 
-  T pMM[R], pGM[R], pMX[R], pXX[R], pMY[R];
-  T pYY0;             // row 0 of the tile may need pYY != pXX (boundary replica)
-  uint32_t padmask;   // bit k: row k of this lane lies above the read
+  T pMM[R], pMX[R], pMY[R];
+  T pGM[RG], pXX[RG];  // general form: per row.  UG: [0] only (pXX[0] = X multiplier of tile row 0)
+  T pYY[UG ? R : 1];   // UG: per-row Y multiplier.  general: [0] = Y multiplier of tile row 0
+  T cXX, cGM;          // UG: launch constants
+  uint32_t padmask;    // bit k: row k of this lane lies above the read
+
+  __device__ __forceinline__ T gm(int k) const { return UG ? cGM : pGM[UG ? 0 : k]; }
+  __device__ __forceinline__ T xx(int k) const { return UG ? (k == 0 ? pXX[0] : cXX) : pXX[UG ? 0 : k]; }
+  __device__ __forceinline__ T yy(int k) const { return UG ? pYY[UG ? k : 0] : (k == 0 ? pYY[0] : pXX[UG ? 0 : k]); }
 
   // Fill constants and this lane's slice of the prior table from the staged read.
   // rs points at the group's staged read blob (planes of Lp bytes); len == 0 => no read.
@@ -147,12 +163,12 @@ struct Tile {
     const uint32_t Lp = round_up16(len);
     const int npad = G * R - (int)len;
     padmask = 0;
-    pYY0 = T(1);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int pos = lig * R + k - npad;
       T pm = T(0), px = T(0);
       int rcode = 6;
+      T xxk, yyk, gmk;
       if (pos >= 0) {
         const uint32_t b = rs[pos];
         const uint32_t q = rs[Lp + pos] & 127u, iq = rs[2 * Lp + pos] & 127u, dq = rs[3 * Lp + pos] & 127u,
@@ -162,17 +178,29 @@ struct Tile {
         px = A::div(e, T(3));
         const uint32_t mn = min(iq, dq), mx = max(iq, dq);
         pMM[k] = mm[((mx * (mx + 1u)) >> 1) + mn];
-        const T pc = lut[cq];
-        pGM[k] = A::sub(T(1), pc);
+        const T pc = UG ? cXX : lut[cq];
+        gmk = A::sub(T(1), pc);
         pMX[k] = lut[iq];
-        pXX[k] = pc;
         pMY[k] = lut[dq];
-        if (k == 0) pYY0 = pc;
+        xxk = pc;
+        yyk = pc;
         rcode = base_code(b);
       } else {
-        pMM[k] = T(0); pGM[k] = T(0); pMX[k] = T(0); pMY[k] = T(0);
-        pXX[k] = (k == 0) ? T(0) : T(1);   // row 0: X forced to 0 whatever arrives; below: X_up is 0 anyway, pYY must be 1
+        // boundary replica: M = 0 (prior 0), X = 0, Y stays K/Lh.  Tile row 0 forces X to 0 whatever
+        // the shuffle delivers; below it X_up is already 0.
+        pMM[k] = T(0); pMX[k] = T(0); pMY[k] = T(0);
+        gmk = T(0);
+        xxk = (k == 0) ? T(0) : T(1);
+        yyk = T(1);
         padmask |= 1u << k;
+      }
+      if constexpr (UG) {
+        pYY[k] = yyk;
+        if (k == 0) { pXX[0] = (pos >= 0) ? cXX : T(0); pGM[0] = cGM; }
+      } else {
+        pGM[k] = gmk;
+        pXX[k] = (k == 0) ? xxk : ((pos >= 0) ? xxk : T(1));
+        if (k == 0) pYY[0] = yyk;
       }
 #pragma unroll
       for (int h = 0; h < 5; ++h) {
@@ -222,14 +250,14 @@ struct Tile {
         const T xd = k ? X[k - 1] : dX;
         const T yd = k ? Y[k - 1] : dY;
         T s = A::mul(md, pMM[k]);
-        s = A::fma(xd, pGM[k], s);
-        s = A::fma(yd, pGM[k], s);
+        s = A::fma(xd, gm(k), s);
+        s = A::fma(yd, gm(k), s);
         nM[k] = A::mul(s, pr[k]);
-        nY[k] = A::fma(Y[k], k ? pXX[k] : pYY0, A::mul(M[k], pMY[k]));
+        nY[k] = A::fma(Y[k], yy(k), A::mul(M[k], pMY[k]));
       }
-      nX[0] = A::fma(uX, pXX[0], A::mul(uM, pMX[0]));
+      nX[0] = A::fma(uX, xx(0), A::mul(uM, pMX[0]));
 #pragma unroll
-      for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], pXX[k], A::mul(nM[k - 1], pMX[k]));
+      for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), A::mul(nM[k - 1], pMX[k]));
       acc = A::add(acc, A::add(nM[R - 1], nX[R - 1]));
       dM = uM; dX = uX; dY = uY;
 #pragma unroll
@@ -269,7 +297,7 @@ __device__ __forceinline__ void emit_f64(const KParams& p, const ReadMeta& rm, u
 // ----------------------------------------------------------------------------------------
 // FP32 main kernel: one task per CTA (<= 32/G reads of a region x a run of its haplotypes).
 // FP64 rerun kernel (LIST): grid-stride over the (read, hap) queue, one pair per lane group.
-template <typename T, int G, int R, bool LIST, int MINB>
+template <typename T, int G, int R, bool LIST, bool UG, int MINB>
 __global__ void __launch_bounds__(32, MINB) phmm_kernel(const KParams p) {
   using L = Layout<T, G, R, LIST>;
   using A = Ar<T>;
@@ -291,7 +319,9 @@ __global__ void __launch_bounds__(32, MINB) phmm_kernel(const KParams p) {
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
   uint32_t parity = 0;
-  Tile<T, G, R> tile;
+  Tile<T, G, R, UG> tile;
+  if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; }
+  else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; }
 
   if constexpr (!LIST) {
     const Task task = p.tasks[blockIdx.x];

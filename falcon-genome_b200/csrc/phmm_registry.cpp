@@ -8,11 +8,12 @@
 namespace fcsphmm {
 
 extern const KernelEntry kEntriesF32G4[], kEntriesF32G8[], kEntriesF32G16[], kEntriesF32G32[];
+extern const KernelEntry kEntriesF32UG4[], kEntriesF32UG8[], kEntriesF32UG16[], kEntriesF32UG32[];
 extern const KernelEntry kEntriesF64G4[], kEntriesF64G8[], kEntriesF64G16[], kEntriesF64G32[];
 
 namespace {
 std::vector<KernelEntry> g_table;
-std::vector<const KernelEntry*> g_sel[2];  // by read length
+std::vector<const KernelEntry*> g_sel[4];  // [f64 * 2 + ug] by read length
 std::once_flag g_once;
 constexpr int kMaxSelLen = 1024;
 
@@ -29,19 +30,20 @@ double class_cost(const KernelEntry& k, int rows_needed) {
 }
 
 void build() {
-  const KernelEntry* lists[] = {kEntriesF32G4,  kEntriesF32G8,  kEntriesF32G16, kEntriesF32G32,
-                                kEntriesF64G4,  kEntriesF64G8,  kEntriesF64G16, kEntriesF64G32};
+  const KernelEntry* lists[] = {kEntriesF32G4,  kEntriesF32G8,  kEntriesF32G16,  kEntriesF32G32,
+                                kEntriesF32UG4, kEntriesF32UG8, kEntriesF32UG16, kEntriesF32UG32,
+                                kEntriesF64G4,  kEntriesF64G8,  kEntriesF64G16,  kEntriesF64G32};
   for (const KernelEntry* l : lists)
     for (; l->G != 0; ++l) g_table.push_back(*l);
-  KernelEntry end = {0, 0, false, nullptr, nullptr, nullptr, 0};
+  KernelEntry end = {0, 0, false, false, nullptr, nullptr, nullptr, 0};
   g_table.push_back(end);
-  for (int f = 0; f < 2; ++f) {
+  for (int f = 0; f < 4; ++f) {
     g_sel[f].assign(kMaxSelLen + 1, nullptr);
     for (int len = 1; len <= kMaxSelLen; ++len) {
       const KernelEntry* best = nullptr;
       double bc = 0;
       for (const KernelEntry& k : g_table) {
-        if (k.G == 0 || k.f64 != (f == 1) || k.G * k.R < len + 1) continue;
+        if (k.G == 0 || k.f64 != (f >= 2) || k.ug != ((f & 1) == 1) || k.G * k.R < len + 1) continue;
         const double c = class_cost(k, len + 1);
         if (!best || c < bc) { best = &k; bc = c; }
       }
@@ -56,16 +58,16 @@ const KernelEntry* kernel_table() {
   return g_table.data();
 }
 
-const KernelEntry* find_kernel(bool f64, int G, int R) {
+const KernelEntry* find_kernel(bool f64, bool ug, int G, int R) {
   for (const KernelEntry* k = kernel_table(); k->G != 0; ++k)
-    if (k->f64 == f64 && k->G == G && k->R == R) return k;
+    if (k->f64 == f64 && k->ug == ug && k->G == G && k->R == R) return k;
   return nullptr;
 }
 
-const KernelEntry* select_kernel(bool f64, int read_len) {
+const KernelEntry* select_kernel(bool f64, bool ug, int read_len) {
   kernel_table();
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
-  return g_sel[f64 ? 1 : 0][read_len];
+  return g_sel[(f64 ? 2 : 0) + (ug ? 1 : 0)][read_len];
 }
 
 }  // namespace fcsphmm

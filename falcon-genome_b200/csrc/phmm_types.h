@@ -71,6 +71,9 @@ struct KParams {
   uint32_t f64_class;      // FP64 kernels: which segment this launch drains
   uint32_t hs_cap;         // u16 entries of haplotype stream in shared memory
   uint32_t hap_stage_bytes;  // bytes of raw haplotype staging in shared memory
+  // uniform-GCP launches: ph2pr[gcp] and 1 - ph2pr[gcp], read from the constant bank
+  float c_xx_f, c_gm_f;
+  double c_xx_d, c_gm_d;
 };
 
 PHMM_HD inline constexpr uint32_t round_up16(uint32_t x) { return (x + 15u) & ~15u; }

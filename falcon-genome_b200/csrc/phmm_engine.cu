@@ -68,6 +68,8 @@ static int uniform_gcp(const uint8_t* c, int32_t len) {
   return diff ? -1 : (int)v;
 }
 
+static cudaError_t init_slot(Slot& s);
+
 int ChunkPlan::launches() const {
   int n = 0;
   if (!force_double)
@@ -131,20 +133,34 @@ int Engine::init(const fcs_phmm_config* cfg) {
     CK(cudaMemcpy(d->d_mm_d, L.mm_d, sizeof(L.mm_d), cudaMemcpyHostToDevice));
     for (const KernelEntry* k = kernel_table(); k->G != 0; ++k) CK(k->set_max_smem(prop.sharedMemPerBlockOptin));
     d->slots.resize(nslots);
-    for (Slot& s : d->slots) {
-      CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-      CK(cudaEventCreate(&s.ev_k0));
-      CK(cudaEventCreate(&s.ev_k1));
-      CK(cudaEventCreate(&s.ev_k2));
-      CK(cudaEventCreate(&s.ev_done));
-    }
+    for (Slot& s : d->slots) CK(init_slot(s));
     devs_.push_back(std::move(d));
   }
   return FCS_PHMM_OK;
 }
 
+static cudaError_t init_slot(Slot& s) {
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  if ((e = cudaEventCreate(&s.ev_k0)) != cudaSuccess) return e;
+  if ((e = cudaEventCreate(&s.ev_k1)) != cudaSuccess) return e;
+  if ((e = cudaEventCreate(&s.ev_k2)) != cudaSuccess) return e;
+  if ((e = cudaEventCreate(&s.ev_done)) != cudaSuccess) return e;
+  if ((e = cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+  for (int i = 0; i < Slot::kSide; ++i) {
+    if ((e = cudaStreamCreateWithFlags(&s.side[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&s.ev_side[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 static void free_slot(Slot& s) {
   if (s.stream) cudaStreamSynchronize(s.stream);
+  for (int i = 0; i < Slot::kSide; ++i) {
+    if (s.side[i]) { cudaStreamSynchronize(s.side[i]); cudaStreamDestroy(s.side[i]); }
+    if (s.ev_side[i]) cudaEventDestroy(s.ev_side[i]);
+  }
+  if (s.ev_fork) cudaEventDestroy(s.ev_fork);
   if (s.h_in) cudaFreeHost(s.h_in);
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.d_buf) cudaFree(s.d_buf);
@@ -522,9 +538,36 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   if (!upload && !P.force_double)  // resident batch: the queues must start empty on every run
     CK(cudaMemsetAsync(s.d_buf + P.off_rcount, 0, kMaxF64Classes * sizeof(uint32_t), s.stream));
   CK(cudaEventRecord(s.ev_k0, s.stream));
+  // Fork: launch i goes to stream i % (1 + kSide); the side streams start after the upload and are
+  // joined before the next phase, so launches of different classes fill each other's tails.
+  auto fork = [&](int n_launches) -> cudaError_t {
+    if (n_launches <= 1) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(s.ev_fork, s.stream);
+    for (int i = 0; i < Slot::kSide && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s.side[i], s.ev_fork, 0);
+    return e;
+  };
+  auto join = [&](int n_launches) -> cudaError_t {
+    if (n_launches <= 1) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < Slot::kSide && e == cudaSuccess; ++i) {
+      e = cudaEventRecord(s.ev_side[i], s.side[i]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s.stream, s.ev_side[i], 0);
+    }
+    return e;
+  };
+  auto pick = [&](int i, int n_launches) { return (n_launches <= 1 || i % (1 + Slot::kSide) == 0) ? s.stream : s.side[i % (1 + Slot::kSide) - 1]; };
   if (!P.force_double) {
-    for (const F32Range& r : P.f32) {
-      if (!r.n_tasks) continue;
+    int nl = 0, li = 0;
+    for (const F32Range& r : P.f32) nl += r.n_tasks ? 1 : 0;
+    CK(fork(nl));
+    // biggest launches first
+    std::vector<const F32Range*> ord;
+    for (const F32Range& r : P.f32)
+      if (r.n_tasks) ord.push_back(&r);
+    std::stable_sort(ord.begin(), ord.end(), [](const F32Range* a, const F32Range* b) {
+      return (uint64_t)a->n_tasks * a->k->G * a->k->R > (uint64_t)b->n_tasks * b->k->G * b->k->R; });
+    for (const F32Range* rp : ord) {
+      const F32Range& r = *rp;
       KParams p;
       fill_kparams(d, s, p, false);
       p.tasks += r.task0;
@@ -535,27 +578,35 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
       const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
       if (smem > 227 * 1024)
         return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype run does not fit in shared memory (" + std::to_string(smem) + " bytes)");
-      CK(r.k->launch(p, r.n_tasks, smem, s.stream));
+      static const size_t smem_pad = (size_t)env_i64("FCS_PHMM_SMEM_PAD", 0);  // developer knob: lowers residency
+      CK(r.k->launch(p, r.n_tasks, smem + smem_pad, pick(li++, nl)));
       stats_.launches += 1;
     }
+    CK(join(nl));
   }
   CK(cudaEventRecord(s.ev_k1, s.stream));
-  for (const F64Range& r : P.f64) {
-    if (!r.cap) continue;
-    KParams p;
-    fill_kparams(d, s, p, true);
-    p.f64_class = r.cls;
-    p.hs_cap = r.hs_cap;
-    p.hap_stage_bytes = r.hap_stage;
-    set_gcp_constants(p, r.k->ug ? P.f64_gcp : -1);
-    const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
-    if (smem > 227 * 1024)
-      return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype too long for the FP64 kernel's shared memory (" + std::to_string(smem) + " bytes)");
-    const unsigned ng = 32 / r.k->G;
-    const unsigned need = (r.cap + ng - 1) / ng;
-    const unsigned resident = (unsigned)d.sm_count * (unsigned)std::max(1, r.k->min_blocks);
-    CK(r.k->launch(p, std::min(need, resident), smem, s.stream));
-    stats_.launches += 1;
+  {
+    int nl = 0, li = 0;
+    for (const F64Range& r : P.f64) nl += r.cap ? 1 : 0;
+    CK(fork(nl));
+    for (const F64Range& r : P.f64) {
+      if (!r.cap) continue;
+      KParams p;
+      fill_kparams(d, s, p, true);
+      p.f64_class = r.cls;
+      p.hs_cap = r.hs_cap;
+      p.hap_stage_bytes = r.hap_stage;
+      set_gcp_constants(p, r.k->ug ? P.f64_gcp : -1);
+      const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
+      if (smem > 227 * 1024)
+        return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype too long for the FP64 kernel's shared memory (" + std::to_string(smem) + " bytes)");
+      const unsigned ng = 32 / r.k->G;
+      const unsigned need = (r.cap + ng - 1) / ng;
+      const unsigned resident = (unsigned)d.sm_count * (unsigned)std::max(1, r.k->min_blocks);
+      CK(r.k->launch(p, std::min(need, resident), smem, pick(li++, nl)));
+      stats_.launches += 1;
+    }
+    CK(join(nl));
   }
   CK(cudaEventRecord(s.ev_k2, s.stream));
   if (download && P.n_pairs) {
@@ -761,11 +812,7 @@ int Engine::batch_create(const fcs_phmm_flat_batch* fb, int device_index, Batch*
   static double dummy_out;
   b->input.reset(new FlatInput(*fb, &dummy_out, nullptr, nullptr));
   Slot& s = b->slot;
-  CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-  CK(cudaEventCreate(&s.ev_k0));
-  CK(cudaEventCreate(&s.ev_k1));
-  CK(cudaEventCreate(&s.ev_k2));
-  CK(cudaEventCreate(&s.ev_done));
+  CK(init_slot(s));
   std::vector<int64_t> regs((size_t)fb->n_regions);
   std::iota(regs.begin(), regs.end(), (int64_t)0);
   size_t next = 0;

@@ -79,6 +79,11 @@ struct ChunkPlan {
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_done = nullptr;
+  // kernels of different classes are forked onto side streams so that their tails overlap
+  static constexpr int kSide = 3;
+  cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_side[kSide] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
   uint8_t* h_in = nullptr;
   size_t h_in_cap = 0;
   uint8_t* h_out = nullptr;

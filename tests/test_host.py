@@ -1,0 +1,100 @@
+"""CPU tests of the host-side logic: flat batches, deterministic generators, region partition
+over ranks (with a world_size-2 gloo run of the shard -> compute -> gather path)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from falcon_genome_b200 import FlatBatch, Region, partition_regions, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_flatbatch_roundtrip():
+    b = synth.tiny_mixed(seed=3)
+    regs = [b.region(g) for g in range(b.n_regions)]
+    b2 = FlatBatch.from_regions(regs)
+    for f in ("read_bases", "read_q", "read_i", "read_d", "read_c", "rd_off", "rd_len", "hap_bases", "hp_off", "hp_len",
+              "reg_read0", "reg_nreads", "reg_hap0", "reg_nhaps", "reg_out0"):
+        assert np.array_equal(getattr(b, f), getattr(b2, f)), f
+    assert b.n_pairs == sum(len(r.reads) * len(r.haps) for r in regs)
+    assert b.cells == sum(sum(len(x[0]) for x in r.reads) * sum(len(h) for h in r.haps) for r in regs)
+
+
+def test_generators_are_deterministic_and_shaped():
+    a, b = synth.config2_uniform(n_regions=3), synth.config2_uniform(n_regions=3)
+    assert np.array_equal(a.read_bases, b.read_bases) and np.array_equal(a.hap_bases, b.hap_bases)
+    assert a.n_pairs == 3000 and set(a.rd_len) == {150} and set(a.hp_len) == {300}
+    assert set(a.read_q) == {30} and set(a.read_i) == {45} and set(a.read_c) == {10}
+    c1 = synth.config1_golden(n_regions=20)
+    assert c1.rd_len.max() == 150 and c1.rd_len.min() >= 60 and 100 <= c1.hp_len.min() and c1.hp_len.max() <= 370
+    assert (c1.read_bases == ord("N")).mean() < 0.03
+    c5 = synth.config5_underflow(n_regions=2)
+    assert set(c5.rd_len) == {250} and set(c5.hp_len) == {1000} and c5.read_q.max() <= 15
+    full = synth.config2_uniform()
+    assert full.n_pairs == 100_000 and full.cells == 4_500_000_000
+
+
+def test_partition_regions_balanced_and_complete():
+    b = synth.config1_golden(n_regions=60, seed=3)
+    cells = b.region_cells()
+    for world in (1, 2, 4, 8):
+        parts = partition_regions(cells, world)
+        allr = np.sort(np.concatenate(parts))
+        assert np.array_equal(allr, np.arange(b.n_regions))
+        loads = np.array([cells[p].sum() for p in parts], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.15
+    assert all(np.array_equal(x, y) for x, y in zip(partition_regions(cells, 4), partition_regions(cells, 4)))
+
+
+def test_select_rebuilds_dense_output_layout():
+    b = synth.tiny_mixed(seed=5, n_regions=8)
+    s = b.select([6, 1, 3])
+    assert s.n_regions == 3 and s.reg_out0[0] == 0
+    assert s.n_pairs == sum(int(b.reg_nreads[g]) * int(b.reg_nhaps[g]) for g in (6, 1, 3))
+    assert s.region(0).haps == b.region(6).haps
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import _pkg; _pkg.load()
+from falcon_genome_b200 import synth, partition_regions
+from oracle import oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+b = synth.tiny_mixed(seed=13, n_regions=9)
+parts = partition_regions(b.region_cells(), world)
+mine = b.select(parts[rank])
+out, used, _, _ = O.batch_simd(mine, 1)      # stand-in for the per-GPU library call
+gathered = [None] * world
+dist.all_gather_object(gathered, (parts[rank].tolist(), out.tolist(), used.tolist()))
+if rank == 0:
+    full = np.full(b.n_pairs, np.nan); fu = np.zeros(b.n_pairs, np.uint8)
+    for ids, o, u in gathered:
+        sub = b.select(ids); o = np.asarray(o); u = np.asarray(u, dtype=np.uint8)
+        for k, g in enumerate(ids):
+            n = int(b.reg_nreads[g]) * int(b.reg_nhaps[g])
+            full[b.reg_out0[g]:b.reg_out0[g]+n] = o[sub.reg_out0[k]:sub.reg_out0[k]+n]
+            fu[b.reg_out0[g]:b.reg_out0[g]+n] = u[sub.reg_out0[k]:sub.reg_out0[k]+n]
+    ref, ru, _, _ = O.batch_simd(b, 1)
+    assert np.array_equal(full, ref) and np.array_equal(fu, ru)
+    print("GLOO-OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_shard_compute_gather(tmp_path):
+    """N>1 host path on CPU: shard regions over 2 ranks (gloo), score each shard independently,
+    gather by region index == single-rank result.  No data-path collective exists."""
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", str(w), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "GLOO-OK" in r.stdout

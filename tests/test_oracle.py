@@ -1,0 +1,127 @@
+"""CPU tests that pin the ORACLE: closed forms, brute-force path enumeration,
+float twin vs double, fallback decision, and the AVX/OpenMP port == scalar twin bit for bit."""
+import math
+
+import numpy as np
+import pytest
+
+from falcon_genome_b200 import FlatBatch, Region, synth
+from helpers import load_golden, parse_kat
+
+
+def rd(bases, q, i=45, d=45, c=10):
+    n = len(bases)
+    f = lambda v: bytes([v] * n) if isinstance(v, int) else bytes(v)  # noqa: E731
+    return (bytes(bases), f(q), f(i), f(d), f(c))
+
+
+def test_kat_closed_forms(oracle):
+    for read, hap, exp in parse_kat():
+        v, used, raw = oracle.pair(read, hap)
+        assert used == 0
+        assert abs(v - exp) < 5e-6
+        assert abs(oracle.log10_double(read, hap) - exp) < 1e-9  # LUT quantisation of matchToMatch only
+
+
+def test_qual_mask_127(oracle):
+    a = oracle.log10_double(rd(b"ACGT", 30), b"ACGT")
+    b = oracle.log10_double((b"ACGT", bytes([30 + 128] * 4), bytes([45 + 128] * 4), bytes([45] * 4), bytes([10 + 128] * 4)), b"ACGT")
+    assert a == b
+
+
+def test_n_matches_everything(oracle):
+    # N scores as a match against every base: on the diagonal it equals the matching read, off the
+    # diagonal it can only add probability mass
+    base = oracle.log10_double(rd(b"ACGTAC", 30), b"ACGTAC")
+    for v in (oracle.log10_double(rd(b"ACNTAC", 30), b"ACGTAC"), oracle.log10_double(rd(b"ACGTAC", 30), b"ACNTAC")):
+        assert base <= v < base + 1e-2
+    assert oracle.log10_double(rd(b"ACGTAC", 30), b"ACTTAC") < base - 2
+    # single cell: exactly the match case
+    assert oracle.log10_double(rd(b"N", 30), b"G") == oracle.log10_double(rd(b"G", 30), b"G") == oracle.log10_double(rd(b"G", 30), b"N")
+
+
+def test_identical_read_closed_form(oracle):
+    # A.5 #5: read == hap, q=40, i=d=45, c=10: diagonal path dominates
+    L = 40
+    seq = bytes(np.random.default_rng(1).choice(list(b"ACGT"), L).astype(np.uint8))
+    v = oracle.log10_double(rd(seq, 40), seq)
+    pmm = 1 - 2 * 10 ** -4.5
+    closed = math.log10(0.9 / L) + L * math.log10(1 - 1e-4) + (L - 1) * math.log10(pmm)
+    assert abs(v - closed) < 1e-3 and v >= closed
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_bruteforce_path_enumeration(oracle, seed):
+    # A.5 #6: explicit sum over all alignments, no DP
+    rng = np.random.default_rng(seed)
+    Lr, Lh = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    bases = bytes(rng.choice(list(b"ACGTN"), Lr).astype(np.uint8))
+    hap = bytes(rng.choice(list(b"ACGTN"), Lh).astype(np.uint8))
+    read = (bases, bytes(rng.integers(2, 42, Lr).astype(np.uint8)), bytes(rng.integers(5, 46, Lr).astype(np.uint8)),
+            bytes(rng.integers(5, 46, Lr).astype(np.uint8)), bytes(rng.integers(5, 30, Lr).astype(np.uint8)))
+    assert abs(oracle.log10_double(read, hap) - oracle.bruteforce_log10(read, hap)) < 1e-12
+
+
+def test_fallback_decision(oracle):
+    # A.5 #7: >= 22 forced mismatches at q=41 push the float sum under 1e-28 -- provided the gap
+    # continuation is expensive too (with gcp 10 a 30-base insertion costs only ~1e-34)
+    hap = b"A" * 60
+    read = rd(b"C" * 30, 41, 45, 45, 40)
+    v, used, raw = oracle.pair(read, hap)
+    assert used == 1 and raw < 1e-28 and math.isfinite(v) and v < -64
+    assert v == oracle.log10_double(read, hap)
+    v2, used2, raw2 = oracle.pair(rd(b"C" * 5, 41, 45, 45, 40), hap)
+    assert used2 == 0 and raw2 >= 1e-28
+    vf, usedf, _ = oracle.pair(rd(b"C" * 5, 41, 45, 45, 40), hap, force_double=True)
+    assert usedf == 1 and abs(vf - v2) < 1e-5
+
+
+def test_float_twin_close_to_double(oracle):
+    b = synth.tiny_mixed(seed=4, n_regions=10)
+    out, used, raw, dbl = oracle.batch_scalar(b)
+    keep = used == 0
+    assert np.abs(out[keep] - dbl[keep]).max() < 5e-5
+    assert np.array_equal(used == 1, raw < np.float32(1e-28))
+
+
+def test_simd_port_bit_identical_to_scalar_twin(oracle):
+    for b in (synth.tiny_mixed(seed=2, n_regions=10), synth.config1_golden(n_regions=3, seed=5)):
+        o1, u1, r1, _ = oracle.batch_scalar(b)
+        o2, u2, r2, nd = oracle.batch_simd(b, 2)
+        assert np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+        assert np.array_equal(u1, u2) and np.array_equal(o1, o2) and nd == int(u1.sum())
+
+
+def test_simd_port_ftz_mode_agrees(oracle):
+    b = synth.config1_golden(n_regions=3, seed=6)
+    o1, u1, _, _ = oracle.batch_simd(b, 2, False)
+    o2, u2, _, _ = oracle.batch_simd(b, 2, True)
+    assert np.array_equal(u1, u2) and np.abs(o1 - o2).max() < 1e-6
+
+
+def test_golden_fixtures_match_oracle(oracle):
+    for name in ("c1_sample.npz", "c5_sample.npz"):
+        b, z = load_golden(name)
+        out, used, raw, dbl = oracle.batch_scalar(b)
+        assert np.array_equal(out, z["out_log10"]) and np.array_equal(used, z["used_fp64"])
+        assert np.array_equal(raw.view(np.uint32), z["raw_f32_bits"]) and np.array_equal(dbl, z["log10_double"])
+    assert load_golden("c5_sample.npz")[1]["used_fp64"].mean() > 0.5
+
+
+def test_order_invariance(oracle):
+    # A.5 #8: per-pair results do not depend on batch order
+    b = synth.tiny_mixed(seed=9, n_regions=6)
+    out, _, _, _ = oracle.batch_scalar(b)
+    perm = [5, 2, 0, 4, 1, 3]
+    bp = b.select(perm)
+    outp, _, _, _ = oracle.batch_scalar(bp)
+    for k, g in enumerate(perm):
+        n = int(b.reg_nreads[g]) * int(b.reg_nhaps[g])
+        assert np.array_equal(out[b.reg_out0[g]:b.reg_out0[g] + n], outp[bp.reg_out0[k]:bp.reg_out0[k] + n])
+
+
+def test_monotone_in_base_quality(oracle):
+    hap = b"ACGTACGTACGTACGT"
+    read_bases = b"ACGTACTTACGTACGT"  # one mismatch
+    vals = [oracle.log10_double(rd(read_bases, q), hap) for q in (10, 20, 30, 40)]
+    assert vals == sorted(vals, reverse=True)

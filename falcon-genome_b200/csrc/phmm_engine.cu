@@ -661,7 +661,7 @@ int Engine::retire_slot(Device& d, Slot& s) {
 int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& regions) {
   std::lock_guard<std::mutex> lk(d.mu);
   CK(cudaSetDevice(d.ordinal));
-  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 1280);
+  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
   size_t next = 0, slot_i = 0;
   int rc = FCS_PHMM_OK;
   while (next < regions.size() && rc == FCS_PHMM_OK) {
@@ -816,7 +816,7 @@ int Engine::batch_create(const fcs_phmm_flat_batch* fb, int device_index, Batch*
   std::vector<int64_t> regs((size_t)fb->n_regions);
   std::iota(regs.begin(), regs.end(), (int64_t)0);
   size_t next = 0;
-  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 1280);
+  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
   Planner pl{*b->input, s, use_double_, keep_raw_, INT64_MAX, hs_cols};
   int rc = pl.run(regs, 0, next);
   if (rc == FCS_PHMM_OK && next != regs.size())

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfcs_pairhmm.so")
+LIB_PATH = os.environ.get("FCS_PHMM_LIB") or os.path.join(_HERE, "libfcs_pairhmm.so")  # env override: developer A/B builds
 
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, EUNSUPPORTED, ETICKET = 0, -1, -2, -3, -4, -5, -6
 ERROR_NAMES = {EINVAL: "EINVAL", ENODEV: "ENODEV", ECUDA: "ECUDA", ENOMEM: "ENOMEM", EUNSUPPORTED: "EUNSUPPORTED", ETICKET: "ETICKET"}

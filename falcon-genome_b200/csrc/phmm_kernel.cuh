@@ -37,7 +37,13 @@
 
 #include "phmm_types.h"
 
+#ifndef PHMM_UNROLL_T
+#define PHMM_UNROLL_T 4
+#endif
+
 namespace fcsphmm {
+
+constexpr int kUnrollT = PHMM_UNROLL_T;  // steps per loop trip (even, so the state arrays rotate without MOVs; 4 measured best: +4 % over 2)
 
 // ----------------------------------------------------------------------------------------
 // arithmetic with pinned rounding and no compiler contraction
@@ -225,7 +231,7 @@ struct Tile {
     T dM = T(0), dX = T(0);
     T dY = __shfl_up_sync(0xffffffffu, Y[R - 1], 1, G);
     T acc = T(0);
-#pragma unroll 2
+#pragma unroll(kUnrollT)
     for (int t = 0; t < nsteps; ++t) {
       const uint32_t hoff = hs_lane[t];
       const uint8_t* prow = tab_lane + hoff * 16u;

@@ -31,8 +31,12 @@ const KernelEntry* select_kernel(bool f64, bool ug, int read_len);
 // (8 CTAs/SM) allow 255 registers, 3 (12/SM) allow 168, 4 (16/SM) allow 128.  A tile needs about
 // 8 registers per row (7 with uniform GCP; twice that in double) plus ~18.
 PHMM_HD inline constexpr int min_blocks_for(int R, int esz, bool ug) {
+#ifdef PHMM_FORCE_MINB
+  return PHMM_FORCE_MINB;
+#else
   const int regs = (ug ? 7 : 8) * R * (esz / 4) + 18;
   return regs <= 126 ? 16 : (regs <= 170 ? 12 : 8);
+#endif
 }
 
 }  // namespace fcsphmm

@@ -45,7 +45,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("cells", C.c_uint64), ("fp64_pairs", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("chunks", C.c_uint64), ("kernel_ms", C.c_double),
-                ("main_kernel_ms", C.c_double)]
+                ("main_kernel_ms", C.c_double), ("host_plan_ms", C.c_double), ("host_pack_ms", C.c_double),
+                ("host_wait_ms", C.c_double), ("host_scatter_ms", C.c_double)]
 
 
 class FlatStruct(C.Structure):

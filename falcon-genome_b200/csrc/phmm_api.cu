@@ -226,7 +226,7 @@ float fcs_pairhmm_lut_mm_f32(int i, int d) { return luts().mm_f[mm_index(i & 127
 double fcs_pairhmm_lut_mm_f64(int i, int d) { return luts().mm_d[mm_index(i & 127, d & 127)]; }
 
 int fcs_pairhmm_kernel_class(int32_t read_len, int32_t fp64, int32_t* lanes_per_read, int32_t* rows_per_lane) {
-  const KernelEntry* k = select_kernel(fp64 != 0, false, read_len);
+  const ClassRef* k = select_class(fp64 != 0, false, read_len);
   if (!k) return set_error(FCS_PHMM_EUNSUPPORTED, "no compiled kernel class covers this read length");
   if (lanes_per_read) *lanes_per_read = k->G;
   if (rows_per_lane) *rows_per_lane = k->R;

@@ -13,7 +13,9 @@
 #include "phmm_engine.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -39,6 +41,9 @@ const char* last_error() { return g_err.c_str(); }
   } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static int64_t env_i64(const char* name, int64_t dflt) {
   const char* v = std::getenv(name);
@@ -46,20 +51,22 @@ static int64_t env_i64(const char* name, int64_t dflt) {
   return std::strtoll(v, nullptr, 10);
 }
 
-// f32 / f64 class ids = position among the f32 / f64 entries of the kernel table
-static std::vector<const KernelEntry*> g_f32_classes, g_f64_classes;
+// class lookup by read length (hot in the planner: one lookup per read)
+static std::vector<const ClassRef*> g_f32_by_len[2];  // [ug]
+static std::vector<int16_t> g_qid_by_len;             // FP64 queue id
 static std::once_flag g_cls_once;
-static void build_class_lists() {
-  // class ids index the GENERAL-form entries; the uniform-GCP twin of a class has the same (G, R)
-  for (const KernelEntry* k = kernel_table(); k->G != 0; ++k)
-    if (!k->ug) (k->f64 ? g_f64_classes : g_f32_classes).push_back(k);
+static void build_len_tables() {
+  for (int ug = 0; ug < 2; ++ug) {
+    g_f32_by_len[ug].assign(1025, nullptr);
+    for (int len = 1; len <= 1024; ++len) g_f32_by_len[ug][len] = select_class(false, ug == 1, len);
+  }
+  g_qid_by_len.assign(1025, -1);
+  for (int len = 1; len <= 1024; ++len)
+    if (const ClassRef* k = select_class(true, false, len)) g_qid_by_len[len] = (int16_t)f64_queue_id(k->G, k->R);
 }
-static int class_id(const KernelEntry* k) {
-  const auto& v = k->f64 ? g_f64_classes : g_f32_classes;
-  for (size_t i = 0; i < v.size(); ++i)
-    if (v[i]->G == k->G && v[i]->R == k->R) return (int)i;
-  return -1;
-}
+static inline const ClassRef* f32_class_of_len(bool ug, int len) { return (len >= 1 && len <= 1024) ? g_f32_by_len[ug ? 1 : 0][len] : nullptr; }
+static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid_by_len[len] : -1; }
+
 // The value all gap-continuation quals of a read share (masked & 127 like the kernels), or -1.
 static int uniform_gcp(const uint8_t* c, int32_t len) {
   const uint8_t v = c[0] & 127u;
@@ -74,7 +81,7 @@ int ChunkPlan::launches() const {
   int n = 0;
   if (!force_double)
     for (const auto& r : f32) n += r.n_tasks ? 1 : 0;
-  for (const auto& r : f64) n += r.cap ? 1 : 0;
+  n += (int)f64.size();
   return n;
 }
 
@@ -89,16 +96,17 @@ int Engine::create(const fcs_phmm_config* cfg, Engine** out) {
 }
 
 int Engine::init(const fcs_phmm_config* cfg) {
-  std::call_once(g_cls_once, build_class_lists);
-  if ((int)g_f64_classes.size() > kMaxF64Classes) return set_error(FCS_PHMM_EINVAL, "too many FP64 kernel classes compiled in");
+  std::call_once(g_cls_once, build_len_tables);
+  if (f64_queue_count() > kMaxF64Classes) return set_error(FCS_PHMM_EINVAL, "too many FP64 kernel classes compiled in");
   fcs_phmm_config c;
   std::memset(&c, 0, sizeof(c));
   if (cfg) std::memcpy(&c, cfg, std::min<size_t>(sizeof(c), cfg->struct_size ? cfg->struct_size : sizeof(c)));
   use_double_ = c.use_double != 0;
   keep_raw_ = c.keep_raw_f32 != 0;
-  pack_threads_ = c.max_threads;
-  max_chunk_cells_ = c.max_chunk_cells > 0 ? c.max_chunk_cells : env_i64("FCS_PHMM_CHUNK_CELLS", 3000000000LL);
-  int nslots = c.slots_per_device > 0 ? c.slots_per_device : 3;
+  pack_threads_ = c.max_threads > 0 ? c.max_threads : (int)env_i64("FCS_PHMM_PACK_THREADS", 4);
+  max_chunk_cells_ = c.max_chunk_cells > 0 ? c.max_chunk_cells : env_i64("FCS_PHMM_CHUNK_CELLS", 0);  // 0 = adaptive
+  // two slots per packing thread: a thread packs into one while its previous chunk is on the device
+  int nslots = std::max(c.slots_per_device > 0 ? c.slots_per_device : 0, 2 * pack_threads_);
 
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -131,7 +139,11 @@ int Engine::init(const fcs_phmm_config* cfg) {
     CK(cudaMemcpy(d->d_mm_f, L.mm_f, sizeof(L.mm_f), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->d_ph2pr_d, L.ph2pr_d, sizeof(L.ph2pr_d), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->d_mm_d, L.mm_d, sizeof(L.mm_d), cudaMemcpyHostToDevice));
-    for (const KernelEntry* k = kernel_table(); k->G != 0; ++k) CK(k->set_max_smem(prop.sharedMemPerBlockOptin));
+    {
+      int nk = 0;
+      const TierKernel* const* tks = tier_kernels(&nk);
+      for (int i = 0; i < nk; ++i) CK(tks[i]->set_max_smem(prop.sharedMemPerBlockOptin));
+    }
     d->slots.resize(nslots);
     for (Slot& s : d->slots) CK(init_slot(s));
     devs_.push_back(std::move(d));
@@ -238,10 +250,11 @@ struct Planner {
     ChunkPlan& P = s.plan;
     P = ChunkPlan();
     P.force_double = force_double;
-    for (auto& b : s.buckets) { b.tasks.clear(); b.hs = 0; b.stage = 0; }
+    for (auto& b : s.buckets) { b.tasks.clear(); b.hs = 0; b.stage = 0; b.cls_mask = 0; }
     s.order.clear();
-    std::vector<uint32_t> f64_cap(g_f64_classes.size(), 0), f64_maxlh(g_f64_classes.size(), 0);
+    std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps;
+    std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
     int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
     size_t reads_bytes = 0, haps_bytes = 0;
     std::vector<uint32_t> lens, hlens;
@@ -266,7 +279,7 @@ struct Planner {
         const InRead r = in.read(g, i);
         if (r.len <= 0 || !r.b || !r.q || !r.i || !r.d || !r.c)
           return set_error(FCS_PHMM_EINVAL, "read with non-positive length or null array");
-        if (!select_kernel(false, false, r.len) || !select_kernel(true, false, r.len))
+        if (!f32_class_of_len(false, r.len) || qid_of_len(r.len) < 0)
           return set_error(FCS_PHMM_EUNSUPPORTED, "read length " + std::to_string(r.len) + " exceeds the compiled kernel classes");
         lens[i] = (uint32_t)r.len;
         gcps[i] = uniform_gcp(r.c, r.len);
@@ -299,26 +312,29 @@ struct Planner {
       // ---- tasks
       const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
       for (int32_t i = 0; i < nr;) {
-        const KernelEntry* kc = select_kernel(false, false, (int)lens[ord[i]]);
-        const int cid = class_id(kc);
-        const int NG = 32 / kc->G;
+        // full groups of the longest remaining read use the table; the last, partly filled group of a
+        // region asks for the class that is cheapest per read actually served
+        const ClassRef* k0 = f32_class_of_len(false, (int)lens[ord[i]]);
+        if (nr - i < 32 / k0->G) k0 = select_class_for(false, false, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
+        const int NG = 32 / k0->G;
         const int cnt = std::min<int32_t>(NG, nr - i);
-        int tg = gcps[ord[i]];  // uniform-GCP launch only if every read of the task shares the value
+        int tg = gcps[ord[i]];  // uniform-GCP form only if every read of the task shares the value
         for (int32_t x = 1; x < cnt; ++x)
           if (gcps[ord[i + x]] != tg) tg = -1;
+        const ClassRef* kc = tg >= 0 ? find_class(false, true, k0->G, k0->R) : k0;
         TaskBucket* bk = nullptr;
         for (auto& b : s.buckets)
-          if (b.cid == cid && b.gcp == tg) { bk = &b; break; }
+          if (b.tk == kc->tk && b.gcp == tg) { bk = &b; break; }
         if (!bk) {
           s.buckets.emplace_back();
           bk = &s.buckets.back();
-          bk->cid = cid;
+          bk->tk = kc->tk;
           bk->gcp = tg;
         }
         for (int32_t j = 0; j < nh;) {
           uint32_t cols = 0, stage = 0;
           int32_t j1 = j;
-          while (j1 < nh && (j1 == j || cols + hlens[j1] + (kc->G - 1) <= hs_cols) && (j1 - j) < 0xffff) {
+          while (j1 < nh && (j1 == j || cols + hlens[j1] + (uint32_t)(kc->G - 1) <= hs_cols) && (j1 - j) < 0xffff) {
             cols += hlens[j1] + (kc->G - 1);
             stage += round_up16(hlens[j1]);
             ++j1;
@@ -329,10 +345,11 @@ struct Planner {
           t.hap0 = hap_base + (uint32_t)j;
           t.n_reads = (uint16_t)cnt;
           t.n_haps = (uint16_t)(j1 - j);
-          t.reserved = 0;
+          t.cls = (uint32_t)kc->cls;
           bk->tasks.push_back(t);
           bk->hs = std::max(bk->hs, cols);
           bk->stage = std::max(bk->stage, stage);
+          bk->cls_mask |= 1ull << kc->cls;
           j = j1;
         }
         i += cnt;
@@ -341,11 +358,12 @@ struct Planner {
       uint32_t maxlh = 0;
       for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
       for (int32_t i = 0; i < nr; ++i) {
-        const int c64 = class_id(select_kernel(true, false, (int)lens[i]));
+        const int c64 = qid_of_len((int)lens[i]);
         f64_cap[c64] += (uint32_t)nh;
         f64_maxlh[c64] = std::max(f64_maxlh[c64], maxlh);
         chunk_gcp = (chunk_gcp == -2) ? gcps[i] : (chunk_gcp == gcps[i] ? chunk_gcp : -1);
       }
+      hap_len_chunk.insert(hap_len_chunk.end(), hlens.begin(), hlens.end());
       P.regions.push_back(g);
       P.reg_out0.push_back(P.n_pairs);
       P.n_reads += nr;
@@ -365,38 +383,100 @@ struct Planner {
     P.off_tasks = off;
     P.n_tasks = 0;
     for (size_t bi = 0; bi < s.buckets.size(); ++bi) {
-      const TaskBucket& b = s.buckets[bi];
+      TaskBucket& b = s.buckets[bi];
       if (b.tasks.empty()) continue;
+      // Order: class by class (rows per lane descending), longest tasks first inside a class.  CTAs
+      // that are resident together then run the same class, i.e. the same unrolled loop body; mixing
+      // classes freely (pure longest-first) thrashes the instruction cache (C3: 2.5 -> 0.9 TCUPS).
+      {
+        const uint32_t n = (uint32_t)b.tasks.size();
+        std::vector<std::pair<uint32_t, uint32_t>> key(n);
+        for (uint32_t t = 0; t < n; ++t) {
+          const Task& x = b.tasks[t];
+          const ClassDesc& cd = b.tk->classes[x.cls];
+          uint32_t cols = 0;
+          for (uint32_t j = 0; j < x.n_haps; ++j) cols += hap_len_chunk[x.hap0 + j] + (uint32_t)cd.G - 1u;
+          key[t] = {(uint32_t)cd.R * cols, t};
+        }
+        std::stable_sort(key.begin(), key.end(), [&](const auto& a, const auto& c) {
+          const Task &ta = b.tasks[a.second], &tc = b.tasks[c.second];
+          if (ta.cls != tc.cls) {
+            const ClassDesc &ca = b.tk->classes[ta.cls], &cc = b.tk->classes[tc.cls];
+            if (ca.R != cc.R) return ca.R > cc.R;
+            return ca.G > cc.G;
+          }
+          return a.first > c.first; });
+        std::vector<Task> sorted(n);
+        for (uint32_t t = 0; t < n; ++t) sorted[t] = b.tasks[key[t].second];
+        b.tasks.swap(sorted);
+        b.max_task_cost = 0;
+        for (uint32_t t = 0; t < n; ++t) b.max_task_cost = std::max(b.max_task_cost, key[t].first);
+      }
       F32Range r;
-      const KernelEntry* gk = g_f32_classes[b.cid];
-      r.k = b.gcp >= 0 ? find_kernel(false, true, gk->G, gk->R) : gk;
-      if (!r.k) r.k = gk;
-      r.gcp = r.k->ug ? b.gcp : -1;
+      r.tk = b.tk;
+      r.gcp = b.tk->ug ? b.gcp : -1;
       r.bucket = (uint32_t)bi;
       r.task0 = (uint32_t)P.n_tasks;
       r.n_tasks = (uint32_t)b.tasks.size();
       r.hs_cap = b.hs;
       r.hap_stage = b.stage;
+      r.max_task_cost = b.max_task_cost;
+      r.smem = 0;
+      for (int c = 0; c < b.tk->n_classes; ++c)
+        if (b.cls_mask >> c & 1ull) r.smem = std::max(r.smem, b.tk->classes[c].smem_bytes(b.hs, b.stage));
       P.f32.push_back(r);
       P.n_tasks += r.n_tasks;
     }
-    P.f64_gcp = chunk_gcp >= 0 ? chunk_gcp : -1;
     off = align_up(off + P.n_tasks * sizeof(Task), 256);
     P.off_rbase = off; off += kMaxF64Classes * sizeof(uint32_t);
     P.off_rcount = off; off += kMaxF64Classes * sizeof(uint32_t);
     off = align_up(off, 256);
     P.off_rerun = off;
-    for (size_t c = 0; c < g_f64_classes.size(); ++c) {
-      if (!f64_cap[c]) continue;
-      F64Range r;
-      r.k = g_f64_classes[c];
-      if (P.f64_gcp >= 0)
-        if (const KernelEntry* uk = find_kernel(true, true, r.k->G, r.k->R)) r.k = uk;
-      r.cls = (uint32_t)c;
-      r.cap = f64_cap[c];
-      r.hs_cap = f64_maxlh[c] + 2u * (uint32_t)(r.k->G - 1);
-      r.hap_stage = round_up16(f64_maxlh[c]);
-      P.f64.push_back(r);
+    P.f64_gcp = chunk_gcp >= 0 ? chunk_gcp : -1;
+    P.f64.clear();
+    // FP64 queues (one per general-form FP64 class) and the launches that drain them: queues whose
+    // class lives in the same tier kernel share a launch.
+    P.queues.clear();
+    for (size_t q = 0; q < f64_cap.size(); ++q) {
+      if (!f64_cap[q]) continue;
+      F64Queue qu;
+      qu.qid = (uint32_t)q;
+      qu.cap = f64_cap[q];
+      qu.maxlh = f64_maxlh[q];
+      P.queues.push_back(qu);
+      const ClassRef* k = f64_queue_class((int)q, P.f64_gcp >= 0);
+      F64Range* rr = nullptr;
+      for (auto& r : P.f64)
+        if (r.tk == k->tk) { rr = &r; break; }
+      if (!rr) {
+        P.f64.emplace_back();
+        rr = &P.f64.back();
+        rr->tk = k->tk;
+        rr->n_seg = 0;
+        rr->hs_cap = 0;
+        rr->hap_stage = 0;
+        rr->smem = 0;
+      }
+      if (rr->n_seg >= 16) return set_error(FCS_PHMM_EINVAL, "internal: more than 16 FP64 classes in one tier");
+      rr->seg_cls[rr->n_seg] = (uint16_t)k->cls;
+      rr->seg_qid[rr->n_seg] = (uint16_t)q;
+      rr->seg_cap[rr->n_seg] = f64_cap[q];
+      rr->seg_G[rr->n_seg] = (uint16_t)k->G;
+      rr->n_seg++;
+      rr->hs_cap = std::max(rr->hs_cap, f64_maxlh[q] + 2u * (uint32_t)(32 - 1));
+      rr->hap_stage = std::max(rr->hap_stage, round_up16(f64_maxlh[q]));
+    }
+    for (auto& r : P.f64) {
+      // hs_cap / hap_stage are per lane group; use each class's own G for the stream padding bound
+      uint32_t hs = 0;
+      for (uint32_t k = 0; k < r.n_seg; ++k) {
+        uint32_t mlh = 0;
+        for (const auto& qu : P.queues)
+          if (qu.qid == r.seg_qid[k]) mlh = qu.maxlh;
+        hs = std::max(hs, mlh + 2u * (uint32_t)(r.seg_G[k] - 1));
+      }
+      r.hs_cap = hs;
+      for (uint32_t k = 0; k < r.n_seg; ++k) r.smem = std::max(r.smem, r.tk->classes[r.seg_cls[k]].smem_bytes(r.hs_cap, r.hap_stage));
     }
     const size_t rerun_bytes = align_up(P.n_pairs * sizeof(RerunEntry), 256);
     if (force_double) { off += rerun_bytes; P.in_bytes = off; }
@@ -434,7 +514,7 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
   std::memset(rcount, 0, kMaxF64Classes * sizeof(uint32_t));
   {
     uint32_t acc = 0;
-    for (const F64Range& r : P.f64) { rbase[r.cls] = acc; acc += r.cap; }
+    for (const F64Queue& q : P.queues) { rbase[q.qid] = acc; acc += q.cap; }
   }
   std::vector<uint32_t> fill(kMaxF64Classes, 0);
   const uint8_t* valid = hap_valid_lut();
@@ -470,7 +550,7 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
         std::memcpy(dst + (size_t)pl * lp, src[pl], (size_t)r.len);
         std::memset(dst + (size_t)pl * lp + r.len, 0, lp - (uint32_t)r.len);
       }
-      const int c64 = class_id(select_kernel(true, false, r.len));
+      const int c64 = qid_of_len(r.len);
       ReadMeta& m = rmeta[ridx];
       m.data_off16 = (uint32_t)(rpos / 16);
       m.len_cls = (uint32_t)r.len | ((uint32_t)c64 << 24);
@@ -487,7 +567,7 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
     opos += nr;
   }
   if (rerun)
-    for (const F64Range& r : P.f64) rcount[r.cls] = fill[r.cls];
+    for (const F64Queue& q : P.queues) rcount[q.qid] = fill[q.qid];
   Task* tasks = reinterpret_cast<Task*>(base + P.off_tasks);
   for (const F32Range& r : P.f32) {
     std::memcpy(tasks + r.task0, s.buckets[r.bucket].tasks.data(), (size_t)r.n_tasks * sizeof(Task));
@@ -512,7 +592,7 @@ void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) 
   p.rerun = reinterpret_cast<RerunEntry*>(b + P.off_rerun);
   p.rerun_count = reinterpret_cast<uint32_t*>(b + P.off_rcount);
   p.rerun_base = reinterpret_cast<const uint32_t*>(b + P.off_rbase);
-  p.f64_class = 0;
+  p.n_seg = 0;
   p.hs_cap = 0;
   p.hap_stage_bytes = 0;
   p.c_xx_f = 0.f; p.c_gm_f = 0.f; p.c_xx_d = 0.0; p.c_gm_d = 0.0;
@@ -564,8 +644,9 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
     std::vector<const F32Range*> ord;
     for (const F32Range& r : P.f32)
       if (r.n_tasks) ord.push_back(&r);
-    std::stable_sort(ord.begin(), ord.end(), [](const F32Range* a, const F32Range* b) {
-      return (uint64_t)a->n_tasks * a->k->G * a->k->R > (uint64_t)b->n_tasks * b->k->G * b->k->R; });
+    // launches whose individual tasks run longest go first, so that they overlap the bulk instead of
+    // starting in its tail
+    std::stable_sort(ord.begin(), ord.end(), [](const F32Range* a, const F32Range* b) { return a->max_task_cost > b->max_task_cost; });
     for (const F32Range* rp : ord) {
       const F32Range& r = *rp;
       KParams p;
@@ -575,35 +656,64 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
       p.hs_cap = r.hs_cap;
       p.hap_stage_bytes = r.hap_stage;
       set_gcp_constants(p, r.gcp);
-      const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
-      if (smem > 227 * 1024)
-        return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype run does not fit in shared memory (" + std::to_string(smem) + " bytes)");
+      if (r.smem > 227 * 1024)
+        return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype run does not fit in shared memory (" + std::to_string(r.smem) + " bytes)");
       static const size_t smem_pad = (size_t)env_i64("FCS_PHMM_SMEM_PAD", 0);  // developer knob: lowers residency
-      CK(r.k->launch(p, r.n_tasks, smem + smem_pad, pick(li++, nl)));
+      static const bool dbg = env_i64("FCS_PHMM_DEBUG", 0) != 0;
+      if (dbg) {
+        std::string cl;
+        const TaskBucket& bk = s.buckets[r.bucket];
+        for (int c = 0; c < r.tk->n_classes; ++c)
+          if (bk.cls_mask >> c & 1ull) {
+            size_t n = 0;
+            for (const Task& t : bk.tasks) n += t.cls == (uint32_t)c;
+            cl += " G" + std::to_string(r.tk->classes[c].G) + "R" + std::to_string(r.tk->classes[c].R) + ":" + std::to_string(n);
+          }
+        // geometric efficiency: useful cells / cells the tiles sweep (32 lanes x R rows x (Lh + G - 1) steps)
+        double swept = 0, useful = 0;
+        const ReadMeta* rm = reinterpret_cast<const ReadMeta*>(s.h_in + P.off_rmeta);
+        const HapMeta* hm = reinterpret_cast<const HapMeta*>(s.h_in + P.off_hmeta);
+        for (const Task& t : bk.tasks) {
+          const ClassDesc& cd = r.tk->classes[t.cls];
+          double cols = 0, hl = 0, rl = 0;
+          for (uint32_t j = 0; j < t.n_haps; ++j) { cols += hm[t.hap0 + j].len + cd.G - 1; hl += hm[t.hap0 + j].len; }
+          for (uint32_t i = 0; i < t.n_reads; ++i) rl += rm[t.read0 + i].len_cls & 0xffffffu;
+          swept += 32.0 * cd.R * cols;
+          useful += rl * hl;
+        }
+        fprintf(stderr, "[fcs_phmm] f32 launch tier %d ug %d gcp %d tasks %u smem %zu hs_cap %u stage %u geom_eff %.3f classes%s\n", r.tk->tier,
+                (int)r.tk->ug, r.gcp, r.n_tasks, r.smem, r.hs_cap, r.hap_stage, useful / swept, cl.c_str());
+      }
+      CK(r.tk->launch(p, r.n_tasks, r.smem + smem_pad, pick(li++, nl)));
       stats_.launches += 1;
     }
     CK(join(nl));
   }
   CK(cudaEventRecord(s.ev_k1, s.stream));
   {
-    int nl = 0, li = 0;
-    for (const F64Range& r : P.f64) nl += r.cap ? 1 : 0;
+    const int nl = (int)P.f64.size();
+    int li = 0;
     CK(fork(nl));
     for (const F64Range& r : P.f64) {
-      if (!r.cap) continue;
       KParams p;
       fill_kparams(d, s, p, true);
-      p.f64_class = r.cls;
       p.hs_cap = r.hs_cap;
       p.hap_stage_bytes = r.hap_stage;
-      set_gcp_constants(p, r.k->ug ? P.f64_gcp : -1);
-      const size_t smem = r.k->smem_bytes(r.hs_cap, r.hap_stage);
-      if (smem > 227 * 1024)
-        return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype too long for the FP64 kernel's shared memory (" + std::to_string(smem) + " bytes)");
-      const unsigned ng = 32 / r.k->G;
-      const unsigned need = (r.cap + ng - 1) / ng;
-      const unsigned resident = (unsigned)d.sm_count * (unsigned)std::max(1, r.k->min_blocks);
-      CK(r.k->launch(p, std::min(need, resident), smem, pick(li++, nl)));
+      set_gcp_constants(p, r.tk->ug ? P.f64_gcp : -1);
+      if (r.smem > 227 * 1024)
+        return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype too long for the FP64 kernel's shared memory (" + std::to_string(r.smem) + " bytes)");
+      const unsigned resident = (unsigned)d.sm_count * (unsigned)std::max(1, r.tk->min_blocks);
+      p.n_seg = r.n_seg;
+      unsigned grid = 0;
+      for (uint32_t k = 0; k < r.n_seg; ++k) {
+        p.seg_cls[k] = r.seg_cls[k];
+        p.seg_qid[k] = r.seg_qid[k];
+        p.seg_cta0[k] = grid;
+        const unsigned ng = 32u / r.seg_G[k];
+        grid += std::min((r.seg_cap[k] + ng - 1) / ng, resident);
+      }
+      p.seg_cta0[r.n_seg] = grid;
+      CK(r.tk->launch(p, grid, r.smem, pick(li++, nl)));
       stats_.launches += 1;
     }
     CK(join(nl));
@@ -623,7 +733,9 @@ int Engine::retire_slot(Device& d, Slot& s) {
   (void)d;
   if (!s.busy) return FCS_PHMM_OK;
   s.busy = false;
+  const double tw0 = now_ms();
   CK(cudaEventSynchronize(s.ev_done));
+  const double tw1 = now_ms();
   const ChunkPlan& P = s.plan;
   float ms_all = 0.f, ms_main = 0.f;
   CK(cudaEventElapsedTime(&ms_all, s.ev_k0, s.ev_k2));
@@ -654,41 +766,119 @@ int Engine::retire_slot(Device& d, Slot& s) {
     std::lock_guard<std::mutex> lk(stats_.mu);
     stats_.kernel_ms += ms_all;
     stats_.main_ms += ms_main;
+    stats_.wait_ms += tw1 - tw0;
+    stats_.scatter_ms += now_ms() - tw1;
   }
   return FCS_PHMM_OK;
 }
 
+// One device: cut the device's regions into chunks, then let `pack_threads_` host threads each
+// plan + pack + launch whole chunks on their own pair of slots (GATK's --native-pair-hmm-threads,
+// /root/reference/src/workers/HTCWorker.cpp:85, maps onto this count).  Packing chunk k+1 overlaps
+// the device work of chunk k, and chunks of different threads overlap on the device.
 int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& regions) {
   std::lock_guard<std::mutex> lk(d.mu);
-  CK(cudaSetDevice(d.ordinal));
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
-  size_t next = 0, slot_i = 0;
-  int rc = FCS_PHMM_OK;
-  while (next < regions.size() && rc == FCS_PHMM_OK) {
-    Slot& s = d.slots[slot_i % d.slots.size()];
-    ++slot_i;
-    rc = retire_slot(d, s);
-    if (rc != FCS_PHMM_OK) break;
-    Planner pl{in, s, use_double_, keep_raw_, max_chunk_cells_, hs_cols};
-    rc = pl.run(regions, next, next);
-    if (rc != FCS_PHMM_OK) break;
-    if (s.plan.n_pairs == 0) continue;
-    rc = ensure_buffers(s, s.plan.in_bytes, s.plan.total_bytes - s.plan.off_out, s.plan.total_bytes);
-    if (rc != FCS_PHMM_OK) break;
-    rc = pack_chunk(s, in);
-    if (rc != FCS_PHMM_OK) break;
-    s.input = &in;
-    rc = launch_chunk(d, s, true, true);
-    if (rc != FCS_PHMM_OK) { cudaStreamSynchronize(s.stream); break; }
-    s.busy = true;
+  // ---- chunk boundaries (cells, pairs and byte limits).  Unless the caller fixed a chunk size, aim
+  // at about two chunks per packing thread: enough to pipeline host packing against the device,
+  // few enough that each kernel launch still has a device-filling number of tasks.
+  std::vector<std::vector<int64_t>> chunks;
+  {
+    std::vector<uint64_t> rc_cells(regions.size()), rc_pairs(regions.size()), rc_bytes(regions.size());
+    uint64_t total = 0;
+    for (size_t k = 0; k < regions.size(); ++k) {
+      const int64_t g = regions[k];
+      int32_t nr = 0, nh = 0;
+      in.shape(g, nr, nh);
+      uint64_t sr = 0, sh = 0;
+      for (int32_t i = 0; i < nr; ++i) sr += (uint64_t)std::max(0, in.read(g, i).len);
+      for (int32_t j = 0; j < nh; ++j) sh += (uint64_t)std::max(0, in.hap(g, j).len);
+      rc_cells[k] = sr * sh;
+      rc_pairs[k] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
+      rc_bytes[k] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
+      total += rc_cells[k];
+    }
+    int64_t limit = max_chunk_cells_;
+    if (limit <= 0) {
+      const int64_t want = (int64_t)(total / (uint64_t)(2 * std::max(1, pack_threads_)));
+      limit = std::min<int64_t>(8000000000LL, std::max<int64_t>(500000000LL, want));
+    }
+    uint64_t cells = 0, pairs = 0, bytes = 0;
+    std::vector<int64_t> cur;
+    // ramp: the first chunk of every packing thread is a quarter of the regular size, so the device
+    // starts early instead of idling while the host packs a full-size first chunk
+    const bool ramp = max_chunk_cells_ <= 0;
+    for (size_t k = 0; k < regions.size(); ++k) {
+      const int64_t lim_now = (ramp && (int)chunks.size() < pack_threads_) ? std::max<int64_t>(limit / 4, 125000000LL) : limit;
+      if (!cur.empty() && cells > 0 &&
+          ((int64_t)(cells + rc_cells[k]) > lim_now || pairs + rc_pairs[k] > 0x7fffffffULL || bytes + rc_bytes[k] > (1ull << 31))) {
+        chunks.emplace_back(std::move(cur));
+        cur.clear();
+        cells = pairs = bytes = 0;
+      }
+      cur.push_back(regions[k]);
+      cells += rc_cells[k]; pairs += rc_pairs[k]; bytes += rc_bytes[k];
+    }
+    if (!cur.empty()) chunks.emplace_back(std::move(cur));
   }
-  const std::string saved = rc != FCS_PHMM_OK ? std::string(last_error()) : std::string();
-  for (Slot& s : d.slots) {
-    int r2 = retire_slot(d, s);
-    if (rc == FCS_PHMM_OK && r2 != FCS_PHMM_OK) rc = r2;
+  const int T = (int)std::max<size_t>(1, std::min<size_t>({(size_t)pack_threads_, chunks.size(), d.slots.size() / 2}));
+  std::atomic<size_t> next_chunk{0};
+  std::atomic<int> first_rc{FCS_PHMM_OK};
+  std::mutex err_mu;
+  std::string err_text;
+  auto fail_with = [&](int rc) {
+    int expect = FCS_PHMM_OK;
+    if (first_rc.compare_exchange_strong(expect, rc)) {
+      std::lock_guard<std::mutex> l2(err_mu);
+      err_text = last_error();
+    }
+  };
+  auto worker = [&](int w) {
+    if (cudaSetDevice(d.ordinal) != cudaSuccess) { set_error(FCS_PHMM_ECUDA, "cudaSetDevice failed"); fail_with(FCS_PHMM_ECUDA); return; }
+    int use = 0;
+    while (first_rc.load() == FCS_PHMM_OK) {
+      const size_t c = next_chunk.fetch_add(1);
+      if (c >= chunks.size()) break;
+      Slot& s = d.slots[(size_t)2 * w + (size_t)(use++ & 1)];
+      int rc = retire_slot(d, s);
+      if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
+      const double t0 = now_ms();
+      size_t next = 0;
+      Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols};
+      rc = pl.run(chunks[c], 0, next);
+      if (rc == FCS_PHMM_OK && next != chunks[c].size()) rc = set_error(FCS_PHMM_EUNSUPPORTED, "a single region exceeds the chunk limits (2^31 pairs / 2 GiB)");
+      if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
+      if (s.plan.n_pairs == 0) continue;
+      rc = ensure_buffers(s, s.plan.in_bytes, s.plan.total_bytes - s.plan.off_out, s.plan.total_bytes);
+      if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
+      const double t1 = now_ms();
+      rc = pack_chunk(s, in);
+      if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
+      {
+        std::lock_guard<std::mutex> lk2(stats_.mu);
+        stats_.plan_ms += t1 - t0;
+        stats_.pack_ms += now_ms() - t1;
+      }
+      s.input = &in;
+      rc = launch_chunk(d, s, true, true);
+      if (rc != FCS_PHMM_OK) { cudaStreamSynchronize(s.stream); fail_with(rc); break; }
+      s.busy = true;
+    }
+    for (int k = 0; k < 2; ++k) {
+      int r2 = retire_slot(d, d.slots[(size_t)2 * w + k]);
+      if (r2 != FCS_PHMM_OK) fail_with(r2);
+    }
+  };
+  if (T == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int w = 1; w < T; ++w) th.emplace_back(worker, w);
+    worker(0);
+    for (auto& t : th) t.join();
   }
-  if (!saved.empty()) set_error(rc, saved);
-  return rc;
+  if (first_rc.load() != FCS_PHMM_OK) return set_error(first_rc.load(), err_text);
+  return FCS_PHMM_OK;
 }
 
 int Engine::compute(const Input& in) {
@@ -912,6 +1102,10 @@ int Engine::get_stats(fcs_phmm_stats* s) {
   std::lock_guard<std::mutex> lk(stats_.mu);
   s->kernel_ms = stats_.kernel_ms;
   s->main_kernel_ms = stats_.main_ms;
+  s->host_plan_ms = stats_.plan_ms;
+  s->host_pack_ms = stats_.pack_ms;
+  s->host_wait_ms = stats_.wait_ms;
+  s->host_scatter_ms = stats_.scatter_ms;
   return FCS_PHMM_OK;
 }
 
@@ -921,6 +1115,7 @@ void Engine::reset_stats() {
   std::lock_guard<std::mutex> lk(stats_.mu);
   stats_.kernel_ms = 0;
   stats_.main_ms = 0;
+  stats_.plan_ms = stats_.pack_ms = stats_.wait_ms = stats_.scatter_ms = 0;
 }
 
 }  // namespace fcsphmm

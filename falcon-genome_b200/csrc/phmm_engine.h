@@ -44,20 +44,32 @@ class Input {
 };
 
 struct F32Range {
-  const KernelEntry* k;
+  const TierKernel* tk;
   uint32_t task0, n_tasks, hs_cap, hap_stage;
   uint32_t bucket;  // index of the TaskBucket the tasks come from
   int gcp;          // >= 0: uniform-GCP launch with this quality, -1: general form
+  size_t smem;      // dynamic shared memory: max over the classes present
+  uint32_t max_task_cost;
 };
-// Tasks of one launch: one kernel class x one gap-continuation value (or -1 = mixed).
+// Tasks of one launch: one tier kernel x one gap-continuation value (or -1 = general form).
 struct TaskBucket {
-  int cid = 0, gcp = -1;
+  const TierKernel* tk = nullptr;
+  int gcp = -1;
   uint32_t hs = 0, stage = 0;
+  uint64_t cls_mask = 0;  // classes of the tier that occur
+  uint32_t max_task_cost = 0;
   std::vector<Task> tasks;
 };
+struct F64Queue {
+  uint32_t qid, cap, maxlh;
+};
+// One FP64 launch: the queues whose class lives in this tier kernel, one CTA segment per queue.
 struct F64Range {
-  const KernelEntry* k;
-  uint32_t cls, cap, hs_cap, hap_stage;
+  const TierKernel* tk;
+  uint32_t n_seg, hs_cap, hap_stage;
+  uint16_t seg_cls[16], seg_qid[16], seg_G[16];
+  uint32_t seg_cap[16];
+  size_t smem;
 };
 
 // Host-side description of one packed chunk (what a slot currently holds).
@@ -71,6 +83,7 @@ struct ChunkPlan {
   size_t n_tasks = 0;
   std::vector<F32Range> f32;
   std::vector<F64Range> f64;
+  std::vector<F64Queue> queues;
   bool force_double = false;
   int f64_gcp = -1;  // >= 0: every read of the chunk shares this gap-continuation quality
   int launches() const;
@@ -113,6 +126,7 @@ struct Stats {
   std::atomic<uint64_t> pairs{0}, cells{0}, fp64_pairs{0}, launches{0}, h2d{0}, d2h{0}, chunks{0};
   std::mutex mu;
   double kernel_ms = 0, main_ms = 0;
+  double plan_ms = 0, pack_ms = 0, wait_ms = 0, scatter_ms = 0;  // host-side phases of compute()
 };
 
 struct Batch;  // device-resident batch

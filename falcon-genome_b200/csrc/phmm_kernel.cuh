@@ -301,14 +301,82 @@ __device__ __forceinline__ void emit_f64(const KParams& p, const ReadMeta& rm, u
 }
 
 // ----------------------------------------------------------------------------------------
-// FP32 main kernel: one task per CTA (<= 32/G reads of a region x a run of its haplotypes).
-// FP64 rerun kernel (LIST): grid-stride over the (read, hap) queue, one pair per lane group.
-template <typename T, int G, int R, bool LIST, bool UG, int MINB>
-__global__ void __launch_bounds__(32, MINB) phmm_kernel(const KParams p) {
-  using L = Layout<T, G, R, LIST>;
+// Task form (FP32 main path): one CTA = one task = <= 32/G reads of a region x a run of its
+// haplotypes, all lane groups streaming the same haplotypes.
+template <typename T, int G, int R, bool UG>
+__device__ __forceinline__ void run_task(const KParams& p, const Task task, uint8_t* smem) {
+  using L = Layout<T, G, R, false>;
+  using A = Ar<T>;
+  const int lane = threadIdx.x;
+  const int grp = lane / G, lig = lane % G;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  T* lut = reinterpret_cast<T*>(smem + L::OFF_LUT);
+  uint8_t* tab_lane = smem + L::OFF_TAB + lane * L::STRIDE;
+  uint8_t* rstage = smem + L::OFF_RSTAGE + grp * L::RSTAGE;
+  const uint32_t hs_bytes = round_up16(p.hs_cap * 2u);
+  uint16_t* hs = reinterpret_cast<uint16_t*>(smem + L::OFF_DYN);
+  uint8_t* hstage = smem + L::OFF_DYN + hs_bytes;
+  const T* __restrict__ mm = reinterpret_cast<const T*>(p.mm);
+
+  for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  Tile<T, G, R, UG> tile;
+  if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; }
+  else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; }
+
+  const bool active = grp < (int)task.n_reads;
+  const uint32_t read = task.read0 + (active ? grp : 0);
+  const ReadMeta rm = p.rmeta[read];
+  const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
+  const HapMeta h_first = p.hmeta[task.hap0];
+  const HapMeta h_last = p.hmeta[task.hap0 + task.n_haps - 1];
+  const uint32_t hap_bytes = (h_last.data_off16 - h_first.data_off16) * 16u + round_up16(h_last.len);
+  // ---- stage reads + haplotypes with TMA bulk copies
+  const uint32_t my_bytes = ((active && lig == 0) ? 5u * round_up16(rlen) : 0u) + (lane == 0 ? hap_bytes : 0u);
+  const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
+  if (lane == 0) mbar_expect_tx(bar, tot);
+  __syncwarp();
+  if (active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
+  if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
+  mbar_wait(bar, 0u);
+  // ---- per-row constants + prior table
+  tile.build(rstage, rlen, lig, lut, mm, tab_lane);
+  // ---- haplotype stream: [G-1 PAD] hap0 [G-1 PAD] hap1 ... [G-1 PAD]
+  uint32_t off = 0;
+  for (uint32_t j = 0; j < task.n_haps; ++j) {
+    const HapMeta hm = p.hmeta[task.hap0 + j];
+    const uint8_t* src = hstage + (hm.data_off16 - h_first.data_off16) * 16u;
+    if (lane < G - 1) hs[off + lane] = (uint16_t)(kCodePad * L::HSCALE);
+    for (uint32_t x = lane; x < hm.len; x += 32) {
+      int c = base_code(src[x]);
+      c = (c > kCodeN) ? kCodePad : c;  // host rejects such haplotypes; never reached
+      hs[off + (G - 1) + x] = (uint16_t)(c * L::HSCALE);
+    }
+    off += (G - 1) + hm.len;
+  }
+  if (lane < G - 1) hs[off + lane] = (uint16_t)(kCodePad * L::HSCALE);
+  __syncwarp();
+  // ---- wavefront over every haplotype of the task
+  off = 0;
+  for (uint32_t j = 0; j < task.n_haps; ++j) {
+    const uint32_t Lh = p.hmeta[task.hap0 + j].len;
+    const T y_init = A::div(A::K(), (T)(int)Lh);
+    const T acc = tile.run(tab_lane, hs + off + (G - 1) - lig, (int)Lh + G - 1, y_init);
+    off += (G - 1) + Lh;
+    if (active && lig == G - 1) {
+      if constexpr (sizeof(T) == 4) emit_f32(p, rm, read, task.hap0 + j, acc);
+      else emit_f64(p, rm, task.hap0 + j, acc);
+    }
+  }
+}
+
+// Queue form (FP64 rerun): CTA `cta` of `nctas` grid-strides over queue `qid`, one pair per lane group.
+template <typename T, int G, int R, bool UG>
+__device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32_t cta, uint32_t nctas, uint8_t* smem) {
+  using L = Layout<T, G, R, true>;
   using A = Ar<T>;
   constexpr int NG = L::NG;
-  extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x;
   const int grp = lane / G, lig = lane % G;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -317,10 +385,12 @@ __global__ void __launch_bounds__(32, MINB) phmm_kernel(const KParams p) {
   uint8_t* rstage = smem + L::OFF_RSTAGE + grp * L::RSTAGE;
   const uint32_t hs_bytes = round_up16(p.hs_cap * 2u);
   const uint32_t hstage_bytes = round_up16(p.hap_stage_bytes);
-  uint16_t* hs = reinterpret_cast<uint16_t*>(smem + L::OFF_DYN) + (LIST ? grp * (hs_bytes / 2u) : 0u);
-  uint8_t* hstage = smem + L::OFF_DYN + (LIST ? NG : 1) * hs_bytes + (LIST ? grp * hstage_bytes : 0u);
+  uint16_t* hs = reinterpret_cast<uint16_t*>(smem + L::OFF_DYN) + grp * (hs_bytes / 2u);
+  uint8_t* hstage = smem + L::OFF_DYN + NG * hs_bytes + grp * hstage_bytes;
   const T* __restrict__ mm = reinterpret_cast<const T*>(p.mm);
 
+  const uint32_t count = p.rerun_count[qid];
+  if (cta * NG >= count) return;
   for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
@@ -328,97 +398,46 @@ __global__ void __launch_bounds__(32, MINB) phmm_kernel(const KParams p) {
   Tile<T, G, R, UG> tile;
   if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; }
   else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; }
-
-  if constexpr (!LIST) {
-    const Task task = p.tasks[blockIdx.x];
-    const bool active = grp < (int)task.n_reads;
-    const uint32_t read = task.read0 + (active ? grp : 0);
-    const ReadMeta rm = p.rmeta[read];
+  const RerunEntry* list = p.rerun + p.rerun_base[qid];
+  for (uint32_t base = cta * NG; base < count; base += nctas * NG) {
+    const bool active = base + grp < count;
+    RerunEntry e;
+    e.read = 0; e.hap = 0;
+    if (active) e = list[base + grp];
+    const ReadMeta rm = p.rmeta[e.read];
+    const HapMeta hm = p.hmeta[e.hap];
     const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
-    const HapMeta h_first = p.hmeta[task.hap0];
-    const HapMeta h_last = p.hmeta[task.hap0 + task.n_haps - 1];
-    const uint32_t hap_bytes = (h_last.data_off16 - h_first.data_off16) * 16u + round_up16(h_last.len);
-    // ---- stage reads + haplotypes with TMA bulk copies
-    const uint32_t my_bytes = ((active && lig == 0) ? 5u * round_up16(rlen) : 0u) + (lane == 0 ? hap_bytes : 0u);
+    const uint32_t Lh = active ? hm.len : 0u;
+    fence_proxy_async();  // staging was read through the generic proxy last round
+    const uint32_t my_bytes = (active && lig == 0) ? 5u * round_up16(rlen) + round_up16(Lh) : 0u;
     const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
     if (lane == 0) mbar_expect_tx(bar, tot);
     __syncwarp();
-    if (active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
-    if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
+    if (active && lig == 0) {
+      bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
+      bulk_g2s(hstage, p.haps + (size_t)hm.data_off16 * 16u, round_up16(Lh), bar);
+    }
     mbar_wait(bar, parity);
     parity ^= 1u;
-    // ---- per-row constants + prior table
     tile.build(rstage, rlen, lig, lut, mm, tab_lane);
-    // ---- haplotype stream: [G-1 PAD] hap0 [G-1 PAD] hap1 ... [G-1 PAD]
-    uint32_t off = 0;
-    for (uint32_t j = 0; j < task.n_haps; ++j) {
-      const HapMeta hm = p.hmeta[task.hap0 + j];
-      const uint8_t* src = hstage + (hm.data_off16 - h_first.data_off16) * 16u;
-      if (lane < G - 1) hs[off + lane] = (uint16_t)(kCodePad * L::HSCALE);
-      for (uint32_t x = lane; x < hm.len; x += 32) {
-        int c = base_code(src[x]);
-        c = (c > kCodeN) ? kCodePad : c;  // host rejects such haplotypes; never reached
-        hs[off + (G - 1) + x] = (uint16_t)(c * L::HSCALE);
+    const uint32_t Lmax = __reduce_max_sync(0xffffffffu, Lh);
+    const uint32_t total = Lmax + 2u * (G - 1);
+    for (uint32_t x = lig; x < total; x += G) {
+      int c = kCodePad;
+      if (x >= (uint32_t)(G - 1) && x < (uint32_t)(G - 1) + Lh) {
+        c = base_code(hstage[x - (G - 1)]);
+        c = (c > kCodeN) ? kCodePad : c;
       }
-      off += (G - 1) + hm.len;
+      hs[x] = (uint16_t)(c * L::HSCALE);
     }
-    if (lane < G - 1) hs[off + lane] = (uint16_t)(kCodePad * L::HSCALE);
     __syncwarp();
-    // ---- wavefront over every haplotype of the task
-    off = 0;
-    for (uint32_t j = 0; j < task.n_haps; ++j) {
-      const uint32_t Lh = p.hmeta[task.hap0 + j].len;
-      const T y_init = A::div(A::K(), (T)(int)Lh);
-      const T acc = tile.run(tab_lane, hs + off + (G - 1) - lig, (int)Lh + G - 1, y_init);
-      off += (G - 1) + Lh;
-      if (active && lig == G - 1) {
-        if constexpr (sizeof(T) == 4) emit_f32(p, rm, read, task.hap0 + j, acc);
-        else emit_f64(p, rm, task.hap0 + j, acc);
-      }
+    const T y_init = A::div(A::K(), (T)(int)(Lh ? Lh : 1u));
+    const T acc = tile.run(tab_lane, hs + (G - 1) - lig, (int)Lmax + G - 1, y_init);
+    if (active && lig == G - 1) {
+      if constexpr (sizeof(T) == 4) emit_f32(p, rm, e.read, e.hap, acc);
+      else emit_f64(p, rm, e.hap, acc);
     }
-  } else {
-    const uint32_t count = p.rerun_count[p.f64_class];
-    const RerunEntry* list = p.rerun + p.rerun_base[p.f64_class];
-    for (uint32_t base = blockIdx.x * NG; base < count; base += gridDim.x * NG) {
-      const bool active = base + grp < count;
-      RerunEntry e;
-      e.read = 0; e.hap = 0;
-      if (active) e = list[base + grp];
-      const ReadMeta rm = p.rmeta[e.read];
-      const HapMeta hm = p.hmeta[e.hap];
-      const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
-      const uint32_t Lh = active ? hm.len : 0u;
-      fence_proxy_async();  // staging was read through the generic proxy last round
-      const uint32_t my_bytes = (active && lig == 0) ? 5u * round_up16(rlen) + round_up16(Lh) : 0u;
-      const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
-      if (lane == 0) mbar_expect_tx(bar, tot);
-      __syncwarp();
-      if (active && lig == 0) {
-        bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
-        bulk_g2s(hstage, p.haps + (size_t)hm.data_off16 * 16u, round_up16(Lh), bar);
-      }
-      mbar_wait(bar, parity);
-      parity ^= 1u;
-      tile.build(rstage, rlen, lig, lut, mm, tab_lane);
-      const uint32_t Lmax = __reduce_max_sync(0xffffffffu, Lh);
-      const uint32_t total = Lmax + 2u * (G - 1);
-      for (uint32_t x = lig; x < total; x += G) {
-        int c = kCodePad;
-        if (x >= (uint32_t)(G - 1) && x < (uint32_t)(G - 1) + Lh) {
-          c = base_code(hstage[x - (G - 1)]);
-          c = (c > kCodeN) ? kCodePad : c;
-        }
-        hs[x] = (uint16_t)(c * L::HSCALE);
-      }
-      __syncwarp();
-      const T y_init = A::div(A::K(), (T)(int)(Lh ? Lh : 1u));
-      const T acc = tile.run(tab_lane, hs + (G - 1) - lig, (int)Lmax + G - 1, y_init);
-      if (active && lig == G - 1) {
-        if constexpr (sizeof(T) == 4) emit_f32(p, rm, e.read, e.hap, acc);
-        else emit_f64(p, rm, e.hap, acc);
-      }
-      __syncwarp();
-    }
+    __syncwarp();
   }
 }
 

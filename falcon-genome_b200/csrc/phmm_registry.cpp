@@ -1,73 +1,109 @@
-// phmm_registry.cpp — gathers the per-translation-unit kernel tables and picks a class
-// (lanes per read G, rows per lane R) for a read length.
+// phmm_registry.cpp — gathers the tier kernels and picks a class (lanes per read G, rows per
+// lane R) for a read length.
 #include "phmm_registry.h"
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
 namespace fcsphmm {
 
-extern const KernelEntry kEntriesF32G4[], kEntriesF32G8[], kEntriesF32G16[], kEntriesF32G32[];
-extern const KernelEntry kEntriesF32UG4[], kEntriesF32UG8[], kEntriesF32UG16[], kEntriesF32UG32[];
-extern const KernelEntry kEntriesF64G4[], kEntriesF64G8[], kEntriesF64G16[], kEntriesF64G32[];
+extern const TierKernel kTierF32T0, kTierF32T1, kTierF32T2, kTierF32UT0, kTierF32UT1, kTierF32UT2;
+extern const TierKernel kTierF64T0, kTierF64T1, kTierF64T2, kTierF64UT0, kTierF64UT1, kTierF64UT2;
 
 namespace {
-std::vector<KernelEntry> g_table;
-std::vector<const KernelEntry*> g_sel[4];  // [f64 * 2 + ug] by read length
-std::once_flag g_once;
+const TierKernel* g_kernels[] = {&kTierF32T0, &kTierF32T1, &kTierF32T2, &kTierF32UT0, &kTierF32UT1, &kTierF32UT2,
+                                 &kTierF64T0, &kTierF64T1, &kTierF64T2, &kTierF64UT0, &kTierF64UT1, &kTierF64UT2};
+constexpr int kNumKernels = 12;
 constexpr int kMaxSelLen = 1024;
+std::vector<ClassRef> g_classes[4];             // [f64 * 2 + ug]
+std::vector<const ClassRef*> g_sel[4];          // by read length
+std::vector<std::pair<int, int>> g_f64_queues;  // (G, R) of the general-form FP64 classes
+std::once_flag g_once;
 
-// Issue slots per useful cell: 8 FMA-pipe instructions + per-step overhead spread over the
-// R rows of a lane, stretched by the wavefront fill/drain (G-1 extra steps on a ~300-column
-// haplotype) and by the rows of the tile the read does not use.
-double class_cost(const KernelEntry& k, int rows_needed) {
-  const int esz = k.f64 ? 8 : 4;
-  const double nv = (k.R * esz + 15) / 16;
-  const double per_cell = 8.0 * (k.f64 ? 2.0 : 1.0) + (7.5 + nv) / k.R;
-  const double skew = 1.0 + (k.G - 1) / 300.0;
-  (void)rows_needed;
-  return (double)(k.G * k.R) * per_cell * skew;  // issue slots per read and haplotype column, x32
+// Issue slots per read and haplotype column (x32): 8 FMA-pipe instructions per cell (x2 in double)
+// plus the per-step overhead spread over the R rows of a lane, stretched by the wavefront
+// fill/drain (G-1 extra steps on a ~300-column haplotype); all G*R rows of the tile are paid for.
+// issue slots of one wavefront step of a warp: R cells x 8 FMA-pipe instructions + per-step overhead
+double step_cost(bool f64, int R) {
+  const int esz = f64 ? 8 : 4;
+  const double nv = (R * esz + 15) / 16;
+  return 8.0 * (f64 ? 2.0 : 1.0) * R + 7.5 + nv;
 }
+double class_cost(bool f64, int G, int R) { return step_cost(f64, R) * G * (1.0 + (G - 1) / 300.0); }
 
 void build() {
-  const KernelEntry* lists[] = {kEntriesF32G4,  kEntriesF32G8,  kEntriesF32G16,  kEntriesF32G32,
-                                kEntriesF32UG4, kEntriesF32UG8, kEntriesF32UG16, kEntriesF32UG32,
-                                kEntriesF64G4,  kEntriesF64G8,  kEntriesF64G16,  kEntriesF64G32};
-  for (const KernelEntry* l : lists)
-    for (; l->G != 0; ++l) g_table.push_back(*l);
-  KernelEntry end = {0, 0, false, false, nullptr, nullptr, nullptr, 0};
-  g_table.push_back(end);
+  for (int i = 0; i < kNumKernels; ++i) {
+    const TierKernel* tk = g_kernels[i];
+    auto& v = g_classes[(tk->f64 ? 2 : 0) + (tk->ug ? 1 : 0)];
+    for (int c = 0; c < tk->n_classes; ++c) v.push_back(ClassRef{tk, c, tk->classes[c].G, tk->classes[c].R});
+  }
   for (int f = 0; f < 4; ++f) {
     g_sel[f].assign(kMaxSelLen + 1, nullptr);
     for (int len = 1; len <= kMaxSelLen; ++len) {
-      const KernelEntry* best = nullptr;
+      const ClassRef* best = nullptr;
       double bc = 0;
-      for (const KernelEntry& k : g_table) {
-        if (k.G == 0 || k.f64 != (f >= 2) || k.ug != ((f & 1) == 1) || k.G * k.R < len + 1) continue;
-        const double c = class_cost(k, len + 1);
+      for (const ClassRef& k : g_classes[f]) {
+        if (k.G * k.R < len + 1) continue;
+        const double c = class_cost(f >= 2, k.G, k.R);
         if (!best || c < bc) { best = &k; bc = c; }
       }
       g_sel[f][len] = best;
     }
   }
+  for (const ClassRef& k : g_classes[2]) g_f64_queues.emplace_back(k.G, k.R);
 }
 }  // namespace
 
-const KernelEntry* kernel_table() {
+const TierKernel* const* tier_kernels(int* n) {
   std::call_once(g_once, build);
-  return g_table.data();
+  if (n) *n = kNumKernels;
+  return g_kernels;
 }
 
-const KernelEntry* find_kernel(bool f64, bool ug, int G, int R) {
-  for (const KernelEntry* k = kernel_table(); k->G != 0; ++k)
-    if (k->f64 == f64 && k->ug == ug && k->G == G && k->R == R) return k;
+const ClassRef* select_class(bool f64, bool ug, int read_len) {
+  std::call_once(g_once, build);
+  if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
+  return g_sel[(f64 ? 2 : 0) + (ug ? 1 : 0)][read_len];
+}
+
+const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, int avg_hap_len) {
+  std::call_once(g_once, build);
+  if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
+  const ClassRef* best = nullptr;
+  double bc = 0;
+  const double lh = avg_hap_len > 0 ? avg_hap_len : 300;
+  for (const ClassRef& k : g_classes[(f64 ? 2 : 0) + (ug ? 1 : 0)]) {
+    if (k.G * k.R < read_len + 1) continue;
+    const int served = std::min(n_reads, 32 / k.G);
+    const double c = step_cost(f64, k.R) * (lh + k.G - 1) / served;
+    if (!best || c < bc * 0.999) { best = &k; bc = c; }
+  }
+  return best;
+}
+
+const ClassRef* find_class(bool f64, bool ug, int G, int R) {
+  std::call_once(g_once, build);
+  for (const ClassRef& k : g_classes[(f64 ? 2 : 0) + (ug ? 1 : 0)])
+    if (k.G == G && k.R == R) return &k;
   return nullptr;
 }
 
-const KernelEntry* select_kernel(bool f64, bool ug, int read_len) {
-  kernel_table();
-  if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
-  return g_sel[(f64 ? 2 : 0) + (ug ? 1 : 0)][read_len];
+int f64_queue_count() {
+  std::call_once(g_once, build);
+  return (int)g_f64_queues.size();
+}
+
+int f64_queue_id(int G, int R) {
+  std::call_once(g_once, build);
+  for (size_t i = 0; i < g_f64_queues.size(); ++i)
+    if (g_f64_queues[i].first == G && g_f64_queues[i].second == R) return (int)i;
+  return -1;
+}
+
+const ClassRef* f64_queue_class(int qid, bool ug) {
+  std::call_once(g_once, build);
+  return find_class(true, ug, g_f64_queues[qid].first, g_f64_queues[qid].second);
 }
 
 }  // namespace fcsphmm

@@ -1,4 +1,5 @@
-// phmm_registry.h — table of compiled kernel classes (lanes per read G x rows per lane R).
+// phmm_registry.h — the compiled kernels: one per (precision, GCP form, register tier), each
+// holding several (lanes per read G, rows per lane R) classes (phmm_tiers.h).
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -8,35 +9,43 @@
 
 namespace fcsphmm {
 
-struct KernelEntry {
+struct ClassDesc {
   int G, R;
-  bool f64;  // double-precision rerun (queue-driven) kernel
-  bool ug;   // uniform gap-continuation quality: pGM / pXX come from the constant bank
-  cudaError_t (*launch)(const KParams& p, unsigned grid, size_t smem, cudaStream_t s);
   size_t (*smem_bytes)(uint32_t hs_cap, uint32_t hap_stage_bytes);
-  cudaError_t (*set_max_smem)(size_t bytes);
-  int min_blocks;  // __launch_bounds__ residency target (CTAs of one warp per SM)
 };
 
-// Every class compiled into the library; terminated by G == 0.
-const KernelEntry* kernel_table();
-const KernelEntry* find_kernel(bool f64, bool ug, int G, int R);
+struct TierKernel {
+  bool f64;        // double-precision, queue-driven rerun kernel
+  bool ug;         // uniform gap-continuation quality: pGM / pXX come from the constant bank
+  int tier;        // 0: 16 CTAs/SM (<=128 regs), 1: 12 (<=168), 2: 8 (<=255)
+  int min_blocks;  // __launch_bounds__ residency target (one-warp CTAs per SM)
+  int n_classes;
+  const ClassDesc* classes;
+  cudaError_t (*launch)(const KParams& p, unsigned grid, size_t smem, cudaStream_t s);
+  cudaError_t (*set_max_smem)(size_t bytes);
+};
 
-// Rows a read of length len needs: len + 1 (one boundary-replica row on top).
-// Picks the cheapest compiled class; returns nullptr when none covers the read.
-const KernelEntry* select_kernel(bool f64, bool ug, int read_len);
+struct ClassRef {
+  const TierKernel* tk;
+  int cls;  // index inside tk->classes == Task::cls / KParams::seg_cls
+  int G, R;
+  size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage) const { return tk->classes[cls].smem_bytes(hs_cap, hap_stage); }
+};
 
-// Residency target (one-warp CTAs per SM).  The register file is split per SM sub-partition
-// (16384 registers each), so the per-thread budget moves in steps: 2 warps per sub-partition
-// (8 CTAs/SM) allow 255 registers, 3 (12/SM) allow 168, 4 (16/SM) allow 128.  A tile needs about
-// 8 registers per row (7 with uniform GCP; twice that in double) plus ~18.
-PHMM_HD inline constexpr int min_blocks_for(int R, int esz, bool ug) {
-#ifdef PHMM_FORCE_MINB
-  return PHMM_FORCE_MINB;
-#else
-  const int regs = (ug ? 7 : 8) * R * (esz / 4) + 18;
-  return regs <= 126 ? 16 : (regs <= 170 ? 12 : 8);
-#endif
-}
+// All compiled kernels (12), terminated by launch == nullptr.
+const TierKernel* const* tier_kernels(int* n);
+// Cheapest class covering a read of this length (rows needed = len + 1) when every lane group of the
+// warp is filled, or nullptr.
+const ClassRef* select_class(bool f64, bool ug, int read_len);
+// Cheapest class per read served when only n_reads (>= 1) reads are left to fill the 32/G lane groups
+// against haplotypes of about avg_hap_len columns: favours wide groups (large G, small R) for leftovers.
+const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, int avg_hap_len);
+const ClassRef* find_class(bool f64, bool ug, int G, int R);
+// FP64 rerun queues are keyed by the (G, R) of the general-form FP64 class of the read.
+int f64_queue_count();
+int f64_queue_id(int G, int R);
+const ClassRef* f64_queue_class(int qid, bool ug);
+
+constexpr int kTierMinBlocks[3] = {16, 12, 8};
 
 }  // namespace fcsphmm

@@ -45,7 +45,7 @@ struct Task {
   uint32_t hap0;
   uint16_t n_reads;
   uint16_t n_haps;
-  uint32_t reserved;
+  uint32_t cls;  // index of the task's (G, R) class inside its register tier (phmm_tiers.h)
 };
 
 struct RerunEntry {
@@ -68,7 +68,12 @@ struct KParams {
   RerunEntry* rerun;       // base of all segments
   uint32_t* rerun_count;   // [kMaxF64Classes]
   const uint32_t* rerun_base;  // [kMaxF64Classes] segment start (entries)
-  uint32_t f64_class;      // FP64 kernels: which segment this launch drains
+  // FP64 launches: the classes of one register tier share a launch; segment k drains queue seg_qid[k]
+  // with tier-local class seg_cls[k] on CTAs [seg_cta0[k], seg_cta0[k+1])
+  uint32_t n_seg;
+  uint16_t seg_cls[16];
+  uint16_t seg_qid[16];
+  uint32_t seg_cta0[17];
   uint32_t hs_cap;         // u16 entries of haplotype stream in shared memory
   uint32_t hap_stage_bytes;  // bytes of raw haplotype staging in shared memory
   // uniform-GCP launches: ph2pr[gcp] and 1 - ph2pr[gcp], read from the constant bank

@@ -94,8 +94,8 @@ typedef struct {
   int32_t n_devices;          /* 0 = every visible device */
   const int32_t* devices;     /* n_devices CUDA ordinals, or NULL for 0..n_devices-1 */
   int32_t use_double;         /* GKL initNative(use_double): force the double path for every pair */
-  int32_t max_threads;        /* GKL initNative(max_threads): host packing threads per device (0 = default) */
-  int32_t slots_per_device;   /* in-flight chunk pipelines (streams) per device, 0 = default (3) */
+  int32_t max_threads;        /* GKL initNative(max_threads): host packing threads per device (0 = default 4) */
+  int32_t slots_per_device;   /* in-flight chunk pipelines (streams) per device; at least 2 per packing thread */
   int64_t max_chunk_cells;    /* split a call into chunks of about this many DP cells, 0 = default */
   int32_t keep_raw_f32;       /* 1 = also return the raw float sums through fcs_pairhmm_compute_flat (tests) */
   int32_t reserved;
@@ -112,6 +112,10 @@ typedef struct {
   uint64_t chunks;
   double kernel_ms;        /* CUDA-event time of the kernels (per chunk: first launch to last), summed */
   double main_kernel_ms;   /* of which: the FP32 wavefront kernels */
+  double host_plan_ms;     /* host phases of fcs_pairhmm_compute, summed over chunks: task planning, */
+  double host_pack_ms;     /*   copying reads/haplotypes into pinned staging,                          */
+  double host_wait_ms;     /*   blocked on the device,                                                */
+  double host_scatter_ms;  /*   scattering results into the caller's arrays                            */
 } fcs_phmm_stats;
 
 /*

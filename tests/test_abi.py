@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Read) == 48 and C.sizeof(_lib.Hap) == 16 and C.sizeof(_lib.RegionStruct) == 48
     assert C.sizeof(_lib.FlatStruct) == 18 * 8
     assert C.sizeof(_lib.Config) == 48
-    assert C.sizeof(_lib.Stats) == 9 * 8
+    assert C.sizeof(_lib.Stats) == 13 * 8
 
 
 def test_luts_bit_identical_to_oracle(oracle):

@@ -58,15 +58,19 @@ def main():
         if a.e2e:
             from falcon_genome_b200 import RegionArray
             ra = RegionArray(b)
-            for _ in range(2):
+            for _ in range(3):
                 h.compute_regions(b, ra)
+            h.reset_stats()
             ts = []
             for _ in range(5):
                 t = time.perf_counter()
                 h.compute_regions(b, ra)
                 ts.append(time.perf_counter() - t)
             t = float(np.median(ts))
-            print(f"  e2e compute(): median {t*1e3:.2f} ms -> {b.cells/t/1e9:.0f} GCUPS; stats {h.stats()}", flush=True)
+            st = h.stats()
+            n = 5.0
+            print(f"  e2e compute(): median {t*1e3:.2f} ms -> {b.cells/t/1e9:.0f} GCUPS; per call: plan {st['host_plan_ms']/n:.2f} pack {st['host_pack_ms']/n:.2f} "
+                  f"wait {st['host_wait_ms']/n:.2f} scatter {st['host_scatter_ms']/n:.2f} kernels {st['kernel_ms']/n:.2f} ms, chunks {st['chunks']/n:.0f}", flush=True)
 
 
 if __name__ == "__main__":

@@ -79,9 +79,11 @@ static cudaError_t init_slot(Slot& s);
 
 int ChunkPlan::launches() const {
   int n = 0;
-  if (!force_double)
+  if (!force_double) {
     for (const auto& r : f32) n += r.n_tasks ? 1 : 0;
-  n += (int)f64.size();
+    n += n_gen ? 1 : 0;
+  }
+  n += (int)f64.size() + (gen64_cap ? 1 : 0);
   return n;
 }
 
@@ -245,6 +247,7 @@ struct Planner {
   bool keep_raw;
   int64_t max_cells;
   uint32_t hs_cols;  // haplotype columns per task (bounds the shared-memory stream)
+  int sm_count = 148;
 
   int run(const std::vector<int64_t>& regions, size_t first, size_t& next) {
     ChunkPlan& P = s.plan;
@@ -252,6 +255,9 @@ struct Planner {
     P.force_double = force_double;
     for (auto& b : s.buckets) { b.tasks.clear(); b.hs = 0; b.stage = 0; b.cls_mask = 0; }
     s.order.clear();
+    s.genlist.clear();
+    s.gen_flags.clear();
+    uint32_t gen64_cap = 0, gen_maxlh = 0;
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps;
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
@@ -279,8 +285,7 @@ struct Planner {
         const InRead r = in.read(g, i);
         if (r.len <= 0 || !r.b || !r.q || !r.i || !r.d || !r.c)
           return set_error(FCS_PHMM_EINVAL, "read with non-positive length or null array");
-        if (!f32_class_of_len(false, r.len) || qid_of_len(r.len) < 0)
-          return set_error(FCS_PHMM_EUNSUPPORTED, "read length " + std::to_string(r.len) + " exceeds the compiled kernel classes");
+        if (r.len > FCS_PHMM_MAX_READ_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "read longer than FCS_PHMM_MAX_READ_LEN");
         lens[i] = (uint32_t)r.len;
         gcps[i] = uniform_gcp(r.c, r.len);
         sum_r += (uint64_t)r.len;
@@ -311,7 +316,20 @@ struct Planner {
       if (!same) std::stable_sort(ord, ord + nr, [&](uint32_t a, uint32_t b) { return lens[a] > lens[b]; });
       // ---- tasks
       const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
+      uint32_t maxlh = 0;
+      for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
+      const bool long_hap = maxlh >= (uint32_t)kGenericMinHapLen;
+      s.gen_flags.resize(read_base + (size_t)nr, 0);
       for (int32_t i = 0; i < nr;) {
+        if (long_hap || lens[ord[i]] > (uint32_t)kGenericMaxSinglePassRead) {
+          // striped generic path: one (read, hap) pair per list entry
+          s.gen_flags[read_base + (size_t)i] = 1;
+          for (int32_t j = 0; j < nh; ++j) s.genlist.push_back(RerunEntry{read_base + (uint32_t)i, hap_base + (uint32_t)j});
+          gen64_cap += (uint32_t)nh;
+          gen_maxlh = std::max(gen_maxlh, maxlh);
+          ++i;
+          continue;
+        }
         // full groups of the longest remaining read use the table; the last, partly filled group of a
         // region asks for the class that is cheapest per read actually served
         const ClassRef* k0 = f32_class_of_len(false, (int)lens[ord[i]]);
@@ -355,9 +373,8 @@ struct Planner {
         i += cnt;
       }
       // ---- FP64 queue capacity per class (worst case: every pair of the read falls back)
-      uint32_t maxlh = 0;
-      for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
       for (int32_t i = 0; i < nr; ++i) {
+        if (long_hap || lens[i] > (uint32_t)kGenericMaxSinglePassRead) continue;  // counted in gen64_cap
         const int c64 = qid_of_len((int)lens[i]);
         f64_cap[c64] += (uint32_t)nh;
         f64_maxlh[c64] = std::max(f64_maxlh[c64], maxlh);
@@ -428,6 +445,10 @@ struct Planner {
       P.n_tasks += r.n_tasks;
     }
     off = align_up(off + P.n_tasks * sizeof(Task), 256);
+    P.off_genlist = off;
+    P.n_gen = (uint32_t)s.genlist.size();
+    P.gen64_cap = gen64_cap;
+    off = align_up(off + (size_t)P.n_gen * sizeof(RerunEntry), 256);
     P.off_rbase = off; off += kMaxF64Classes * sizeof(uint32_t);
     P.off_rcount = off; off += kMaxF64Classes * sizeof(uint32_t);
     off = align_up(off, 256);
@@ -481,6 +502,18 @@ struct Planner {
     const size_t rerun_bytes = align_up(P.n_pairs * sizeof(RerunEntry), 256);
     if (force_double) { off += rerun_bytes; P.in_bytes = off; }
     else { P.in_bytes = off; off += rerun_bytes; }
+    // per-CTA boundary rows of the striped kernels (3 planes of up to 8-byte values per CTA)
+    P.gen_ctas = 0;
+    P.scratch_cols = 0;
+    P.off_scratch = off;
+    if (P.n_gen) {
+      P.scratch_cols = (gen_maxlh + 31u) / 32u * 32u + 32u;
+      const size_t per_cta = (size_t)3 * P.scratch_cols * sizeof(double);
+      size_t ctas = std::min<size_t>((size_t)sm_count * 4, std::max<size_t>(1, ((size_t)256 << 20) / per_cta));
+      ctas = std::min<size_t>(ctas, std::max<uint32_t>(P.n_gen, 1u));
+      P.gen_ctas = (uint32_t)ctas;
+      off = align_up(off + ctas * per_cta, 256);
+    }
     P.off_out = off; off += P.n_pairs * sizeof(double);
     P.off_raw = off; if (keep_raw) off += P.n_pairs * sizeof(float);
     P.off_used = off; off += P.n_pairs;
@@ -515,6 +548,7 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
   {
     uint32_t acc = 0;
     for (const F64Queue& q : P.queues) { rbase[q.qid] = acc; acc += q.cap; }
+    rbase[kQueueGenericF64] = acc;
   }
   std::vector<uint32_t> fill(kMaxF64Classes, 0);
   const uint8_t* valid = hap_valid_lut();
@@ -550,7 +584,7 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
         std::memcpy(dst + (size_t)pl * lp, src[pl], (size_t)r.len);
         std::memset(dst + (size_t)pl * lp + r.len, 0, lp - (uint32_t)r.len);
       }
-      const int c64 = qid_of_len(r.len);
+      const int c64 = s.gen_flags[ridx] ? kQueueGenericF64 : qid_of_len(r.len);
       ReadMeta& m = rmeta[ridx];
       m.data_off16 = (uint32_t)(rpos / 16);
       m.len_cls = (uint32_t)r.len | ((uint32_t)c64 << 24);
@@ -566,8 +600,11 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
     }
     opos += nr;
   }
-  if (rerun)
+  if (rerun) {
     for (const F64Queue& q : P.queues) rcount[q.qid] = fill[q.qid];
+    rcount[kQueueGenericF64] = fill[kQueueGenericF64];
+  }
+  if (P.n_gen) std::memcpy(base + P.off_genlist, s.genlist.data(), (size_t)P.n_gen * sizeof(RerunEntry));
   Task* tasks = reinterpret_cast<Task*>(base + P.off_tasks);
   for (const F32Range& r : P.f32) {
     std::memcpy(tasks + r.task0, s.buckets[r.bucket].tasks.data(), (size_t)r.n_tasks * sizeof(Task));
@@ -593,6 +630,10 @@ void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) 
   p.rerun_count = reinterpret_cast<uint32_t*>(b + P.off_rcount);
   p.rerun_base = reinterpret_cast<const uint32_t*>(b + P.off_rbase);
   p.n_seg = 0;
+  p.gen_list = reinterpret_cast<const RerunEntry*>(b + P.off_genlist);
+  p.gen_count = P.n_gen;
+  p.scratch_cols = P.scratch_cols;
+  p.scratch = b + P.off_scratch;
   p.hs_cap = 0;
   p.hap_stage_bytes = 0;
   p.c_xx_f = 0.f; p.c_gm_f = 0.f; p.c_xx_d = 0.0; p.c_gm_d = 0.0;
@@ -637,9 +678,15 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   };
   auto pick = [&](int i, int n_launches) { return (n_launches <= 1 || i % (1 + Slot::kSide) == 0) ? s.stream : s.side[i % (1 + Slot::kSide) - 1]; };
   if (!P.force_double) {
-    int nl = 0, li = 0;
+    int nl = P.n_gen ? 1 : 0, li = 0;
     for (const F32Range& r : P.f32) nl += r.n_tasks ? 1 : 0;
     CK(fork(nl));
+    if (P.n_gen) {  // striped generic kernel first: its pairs are the longest-running work items
+      KParams p;
+      fill_kparams(d, s, p, false);
+      CK(launch_generic_f32(p, P.gen_ctas, pick(li++, nl)));
+      stats_.launches += 1;
+    }
     // biggest launches first
     std::vector<const F32Range*> ord;
     for (const F32Range& r : P.f32)
@@ -691,9 +738,15 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   }
   CK(cudaEventRecord(s.ev_k1, s.stream));
   {
-    const int nl = (int)P.f64.size();
+    const int nl = (int)P.f64.size() + (P.gen64_cap ? 1 : 0);
     int li = 0;
     CK(fork(nl));
+    if (P.gen64_cap) {
+      KParams p;
+      fill_kparams(d, s, p, true);
+      CK(launch_generic_f64(p, std::min(P.gen_ctas, P.gen64_cap), pick(li++, nl)));
+      stats_.launches += 1;
+    }
     for (const F64Range& r : P.f64) {
       KParams p;
       fill_kparams(d, s, p, true);
@@ -844,7 +897,7 @@ int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& r
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
       const double t0 = now_ms();
       size_t next = 0;
-      Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols};
+      Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count};
       rc = pl.run(chunks[c], 0, next);
       if (rc == FCS_PHMM_OK && next != chunks[c].size()) rc = set_error(FCS_PHMM_EUNSUPPORTED, "a single region exceeds the chunk limits (2^31 pairs / 2 GiB)");
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
@@ -1007,7 +1060,7 @@ int Engine::batch_create(const fcs_phmm_flat_batch* fb, int device_index, Batch*
   std::iota(regs.begin(), regs.end(), (int64_t)0);
   size_t next = 0;
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
-  Planner pl{*b->input, s, use_double_, keep_raw_, INT64_MAX, hs_cols};
+  Planner pl{*b->input, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count};
   int rc = pl.run(regs, 0, next);
   if (rc == FCS_PHMM_OK && next != regs.size())
     rc = set_error(FCS_PHMM_EUNSUPPORTED, "batch too large for one resident chunk (2^31 pairs / 2 GiB of reads+haplotypes)");

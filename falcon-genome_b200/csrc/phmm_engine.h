@@ -81,6 +81,8 @@ struct ChunkPlan {
   size_t off_rerun = 0, in_bytes = 0;  // input part = [0, in_bytes)
   size_t off_out = 0, off_used = 0, off_raw = 0, total_bytes = 0;
   size_t n_tasks = 0;
+  size_t off_genlist = 0, off_scratch = 0;
+  uint32_t n_gen = 0, gen64_cap = 0, gen_ctas = 0, scratch_cols = 0;  // striped generic path
   std::vector<F32Range> f32;
   std::vector<F64Range> f64;
   std::vector<F64Queue> queues;
@@ -109,6 +111,8 @@ struct Slot {
   // packer scratch (reused)
   std::vector<TaskBucket> buckets;
   std::vector<uint32_t> order;
+  std::vector<RerunEntry> genlist;     // (read, hap) pairs of the striped generic path
+  std::vector<uint8_t> gen_flags;      // per chunk-wide read: takes the generic path
 };
 
 struct Device {

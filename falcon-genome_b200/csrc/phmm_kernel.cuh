@@ -164,10 +164,12 @@ struct Tile {
 
   // Fill constants and this lane's slice of the prior table from the staged read.
   // rs points at the group's staged read blob (planes of Lp bytes); len == 0 => no read.
+  // row0 / npad: tile row 0 of lane 0 is row `row0` of a striped read whose first `npad` rows are
+  // boundary replicas (single pass: row0 = 0, npad = G*R - len).
   __device__ __forceinline__ void build(const uint8_t* rs, uint32_t len, int lig, const T* lut, const T* __restrict__ mm,
-                                        uint8_t* tab_lane) {
+                                        uint8_t* tab_lane, int row0 = 0, int npad_override = -1) {
     const uint32_t Lp = round_up16(len);
-    const int npad = G * R - (int)len;
+    const int npad = (npad_override >= 0 ? npad_override : G * R - (int)len) - row0;
     padmask = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -218,58 +220,76 @@ struct Tile {
     }
   }
 
+  // DP state of the tile at the column processed last: R rows of (M, X, Y), the values received
+  // from the lane above one step ago (= the diagonal inputs of tile row 0) and the running sum.
+  struct State {
+    T M[R], X[R], Y[R];
+    T dM, dX, dY;
+    T acc;
+  };
+
+  __device__ __forceinline__ void init(State& st, T y_init) const {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      st.M[k] = T(0);
+      st.X[k] = T(0);
+      st.Y[k] = ((padmask >> k) & 1u) ? y_init : T(0);
+    }
+    st.dM = T(0);
+    st.dX = T(0);
+    st.dY = __shfl_up_sync(0xffffffffu, st.Y[R - 1], 1, G);
+    st.acc = T(0);
+  }
+
+  // One column.  prow = this lane's slice of the prior table for the symbol of its column;
+  // (uM, uX, uY) = bottom row of the lane above at the same column (it finished it one step ago).
+  __device__ __forceinline__ void step(State& st, const uint8_t* prow, T uM, T uX, T uY) const {
+    T pr[NV * VW];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 f = *reinterpret_cast<const float4*>(prow + v * 16);
+        pr[v * 4 + 0] = f.x; pr[v * 4 + 1] = f.y; pr[v * 4 + 2] = f.z; pr[v * 4 + 3] = f.w;
+      } else {
+        const double2 f = *reinterpret_cast<const double2*>(prow + v * 16);
+        pr[v * 2 + 0] = f.x; pr[v * 2 + 1] = f.y;
+      }
+    }
+    T nM[R], nX[R], nY[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const T md = k ? st.M[k - 1] : st.dM;
+      const T xd = k ? st.X[k - 1] : st.dX;
+      const T yd = k ? st.Y[k - 1] : st.dY;
+      T s = A::mul(md, pMM[k]);
+      s = A::fma(xd, gm(k), s);
+      s = A::fma(yd, gm(k), s);
+      nM[k] = A::mul(s, pr[k]);
+      nY[k] = A::fma(st.Y[k], yy(k), A::mul(st.M[k], pMY[k]));
+    }
+    nX[0] = A::fma(uX, xx(0), A::mul(uM, pMX[0]));
+#pragma unroll
+    for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), A::mul(nM[k - 1], pMX[k]));
+    st.acc = A::add(st.acc, A::add(nM[R - 1], nX[R - 1]));
+    st.dM = uM; st.dX = uX; st.dY = uY;
+#pragma unroll
+    for (int k = 0; k < R; ++k) { st.M[k] = nM[k]; st.X[k] = nX[k]; st.Y[k] = nY[k]; }
+  }
+
   // One haplotype.  hs_lane[t] is the symbol offset (in 16-byte units) of the column this
   // lane sees at step t.  Returns sum over columns of (M + X) of this lane's bottom row.
   __device__ __forceinline__ T run(const uint8_t* tab_lane, const uint16_t* hs_lane, int nsteps, T y_init) const {
-    T M[R], X[R], Y[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      M[k] = T(0);
-      X[k] = T(0);
-      Y[k] = ((padmask >> k) & 1u) ? y_init : T(0);
-    }
-    T dM = T(0), dX = T(0);
-    T dY = __shfl_up_sync(0xffffffffu, Y[R - 1], 1, G);
-    T acc = T(0);
+    State st;
+    init(st, y_init);
 #pragma unroll(kUnrollT)
     for (int t = 0; t < nsteps; ++t) {
       const uint32_t hoff = hs_lane[t];
-      const uint8_t* prow = tab_lane + hoff * 16u;
-      T pr[NV * VW];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        if constexpr (sizeof(T) == 4) {
-          const float4 f = *reinterpret_cast<const float4*>(prow + v * 16);
-          pr[v * 4 + 0] = f.x; pr[v * 4 + 1] = f.y; pr[v * 4 + 2] = f.z; pr[v * 4 + 3] = f.w;
-        } else {
-          const double2 f = *reinterpret_cast<const double2*>(prow + v * 16);
-          pr[v * 2 + 0] = f.x; pr[v * 2 + 1] = f.y;
-        }
-      }
-      const T uM = __shfl_up_sync(0xffffffffu, M[R - 1], 1, G);
-      const T uX = __shfl_up_sync(0xffffffffu, X[R - 1], 1, G);
-      const T uY = __shfl_up_sync(0xffffffffu, Y[R - 1], 1, G);
-      T nM[R], nX[R], nY[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const T md = k ? M[k - 1] : dM;
-        const T xd = k ? X[k - 1] : dX;
-        const T yd = k ? Y[k - 1] : dY;
-        T s = A::mul(md, pMM[k]);
-        s = A::fma(xd, gm(k), s);
-        s = A::fma(yd, gm(k), s);
-        nM[k] = A::mul(s, pr[k]);
-        nY[k] = A::fma(Y[k], yy(k), A::mul(M[k], pMY[k]));
-      }
-      nX[0] = A::fma(uX, xx(0), A::mul(uM, pMX[0]));
-#pragma unroll
-      for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), A::mul(nM[k - 1], pMX[k]));
-      acc = A::add(acc, A::add(nM[R - 1], nX[R - 1]));
-      dM = uM; dX = uX; dY = uY;
-#pragma unroll
-      for (int k = 0; k < R; ++k) { M[k] = nM[k]; X[k] = nX[k]; Y[k] = nY[k]; }
+      const T uM = __shfl_up_sync(0xffffffffu, st.M[R - 1], 1, G);
+      const T uX = __shfl_up_sync(0xffffffffu, st.X[R - 1], 1, G);
+      const T uY = __shfl_up_sync(0xffffffffu, st.Y[R - 1], 1, G);
+      step(st, tab_lane + hoff * 16u, uM, uX, uY);
     }
-    return acc;
+    return st.acc;
   }
 };
 

@@ -48,4 +48,10 @@ const ClassRef* f64_queue_class(int qid, bool ug);
 
 constexpr int kTierMinBlocks[3] = {16, 12, 8};
 
+// striped generic kernels (phmm_generic.cuh): any read / haplotype length
+cudaError_t launch_generic_f32(const KParams& p, unsigned grid, cudaStream_t s);
+cudaError_t launch_generic_f64(const KParams& p, unsigned grid, cudaStream_t s);
+constexpr int kGenericMaxSinglePassRead = 383;  // longer reads take the striped path (FP64 single-pass tiles end at 384 rows)
+constexpr int kGenericMinHapLen = 2001;         // regions with a longer haplotype take the striped path
+
 }  // namespace fcsphmm

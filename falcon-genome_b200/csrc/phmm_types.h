@@ -25,6 +25,7 @@ constexpr int kTabRows = 6;  // haplotype symbol classes: A C G T N PAD
 constexpr int kCodeN = 4;
 constexpr int kCodePad = 5;
 constexpr int kMaxF64Classes = 40;
+constexpr int kQueueGenericF64 = kMaxF64Classes - 1;  // FP64 rerun queue of the striped generic path
 
 struct ReadMeta {
   uint32_t data_off16;  // offset of the read blob in `reads`, in 16-byte units
@@ -76,6 +77,11 @@ struct KParams {
   uint32_t seg_cta0[17];
   uint32_t hs_cap;         // u16 entries of haplotype stream in shared memory
   uint32_t hap_stage_bytes;  // bytes of raw haplotype staging in shared memory
+  // generic (striped) path: host-built pair list for the FP32 pass, per-CTA boundary scratch rows
+  const RerunEntry* gen_list;
+  uint32_t gen_count;
+  uint32_t scratch_cols;  // columns per scratch plane (3 planes of T per CTA)
+  void* scratch;
   // uniform-GCP launches: ph2pr[gcp] and 1 - ph2pr[gcp], read from the constant bank
   float c_xx_f, c_gm_f;
   double c_xx_d, c_gm_d;

@@ -152,15 +152,38 @@ def test_golden_fixtures(hmm):
         assert abs(hmm.compute_likelihoods([read], [hap])[0, 0] - exp) < 5e-6
 
 
-def test_long_reads_are_refused_not_mangled(hmm):
-    """Reads beyond the compiled single-pass classes: an error code, never a silent wrong answer."""
-    from falcon_genome_b200 import PairHMMError
+def test_long_reads_and_long_haplotypes_striped_path(hmm, oracle):
+    """Shapes beyond the single-pass tiles (reads > 383 rows, haplotypes > 2000 columns) take the
+    striped generic kernels: same bit-level contract, including the FP64 fallback."""
+    rng = np.random.default_rng(17)
 
-    L = 1500
-    rd = (b"A" * L, bytes([30] * L), bytes([45] * L), bytes([45] * L), bytes([10] * L))
-    with pytest.raises(PairHMMError) as e:
-        hmm.compute_likelihoods([rd], [b"ACGT" * 50])
-    assert e.value.code == -5
+    def seq(n):
+        return bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+
+    def read_from(h, L, q_lo=6, q_hi=42):
+        s0 = int(rng.integers(0, max(1, len(h) - L)))
+        b = bytearray((h * (L // len(h) + 2))[s0:s0 + L])
+        for k in rng.integers(0, L, max(1, L // 50)):
+            b[k] = ord("ACGT"[int(rng.integers(0, 4))])
+        return (bytes(b), bytes(rng.integers(q_lo, q_hi, L).astype(np.uint8)), bytes(rng.integers(20, 46, L).astype(np.uint8)),
+                bytes(rng.integers(20, 46, L).astype(np.uint8)), bytes(rng.integers(8, 12, L).astype(np.uint8)))
+
+    h1, h2, h3 = seq(900), seq(2500), seq(333)
+    regs = [
+        Region([read_from(h1, L) for L in (384, 511, 512, 513, 767, 1023, 1024, 1025, 1500)], [h1, h1[:300], h3]),
+        Region([(h1[:L], bytes([30] * L), bytes([45] * L), bytes([45] * L), bytes([10] * L)) for L in (256, 512, 768)], [h1]),  # padding fills a stripe exactly; alignment starts at column 1
+        Region([read_from(h2, L) for L in (5, 150, 400, 1200)], [h2, h2[100:2300], h3]),   # long haplotypes
+        Region([read_from(h3, 150), read_from(h1, 600, 2, 8)], [h3, seq(700)]),               # mixed with a normal read; low quals -> FP64
+    ]
+    b = FlatBatch.from_regions(regs)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+    assert used.any() and not used.all()
+    with PairHMM(use_double=True) as hd:
+        outd, usedd = hd.compute_flat(b)
+    _, _, _, dbl = oracle.batch_scalar(b)
+    fin = np.isfinite(dbl)  # some pairs underflow even the 2^1020-scaled double: -inf on both sides
+    assert usedd.all() and np.array_equal(fin, np.isfinite(outd)) and np.abs(outd[fin] - dbl[fin]).max() <= 1e-9
 
 
 def test_batching_invariance(hmm):

@@ -30,6 +30,9 @@ __global__ void k(float* out, const float* in, long long* cyc, float kc) {
       if (V == 6) { a2[i] = __ffma2_rn(x2[i], y2[i], a2[i]); x2[i] = __fmul2_rn(x2[i], y2[(i + 1) % N]); }
       if (V == 7) a[i] = __fmaf_rn(x[i], c, a[i]);                           // 2 distinct + shared c
       if (V == 8) a[i] = __fadd_rn(a[i], x[i]);
+      if (V == 11) { a[i] = __fmul_rn(a[i], y[i]); x[i] = __fmul_rn(x[i], y[i]); }      // two FMULs sharing y[i]
+      if (V == 12) { a[i] = __fmaf_rn(a[i], y[i], kc); x[i] = __fmaf_rn(x[i], y[i], kc); } // two FFMAs sharing y[i], const addend
+      if (V == 13) { float t0 = __fmul_rn(a[i], y[i]); float t1 = __fmul_rn(x[i], y[i]); a[i] = __fmaf_rn(x[i], kc, t0); x[i] = __fmaf_rn(a[i], kc, t1); }
       if (V == 9) a[i] = __fmaf_rn(x[i], kc, a[i]);                          // constant-bank operand
       if (V == 10) { a[i] = __fmaf_rn(x[i], kc, a[i]); x[i] = __fmul_rn(x[i], y[i]); }
     }
@@ -79,6 +82,9 @@ int main() {
   run<8>("FADD  r,r", N, out, in, cyc);
   run<9>("FFMA  r,const,r", N, out, in, cyc);
   run<10>("FFMA r,const,r + FMUL r,r", 2 * N, out, in, cyc);
+  run<11>("2x FMUL sharing one operand", 2 * N, out, in, cyc);
+  run<12>("2x FFMA r,shared,const", 2 * N, out, in, cyc);
+  run<13>("pairs: 2 FMUL shared + 2 FFMA const", 4 * N, out, in, cyc);
   run<3>("FFMA2 rr,rr,rr", N, out, in, cyc);
   run<4>("FMUL2 rr,rr", N, out, in, cyc);
   run<5>("FFMA+FMUL mix", 2 * N, out, in, cyc);

@@ -315,6 +315,11 @@ struct Planner {
       for (int32_t i = 1; i < nr && same; ++i) same = lens[i] == lens[0];
       if (!same) std::stable_sort(ord, ord + nr, [&](uint32_t a, uint32_t b) { return lens[a] > lens[b]; });
       // ---- tasks
+      // Tail shaping: the last quarter of a chunk's regions is cut into tasks of half the haplotype
+      // columns.  Tasks are launched longest first, so the short ones fill the end of the grid and
+      // the last wave of CTAs is half as long (equal-size tasks finish in lock step otherwise).
+      static const int tail_pct = (int)env_i64("FCS_PHMM_TAIL_PCT", 25);
+      const uint32_t cols_limit = (k - first) * 100 >= (regions.size() - first) * (size_t)(100 - tail_pct) ? std::max(hs_cols / 2, 1u) : hs_cols;
       const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
       uint32_t maxlh = 0;
       for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
@@ -352,7 +357,7 @@ struct Planner {
         for (int32_t j = 0; j < nh;) {
           uint32_t cols = 0, stage = 0;
           int32_t j1 = j;
-          while (j1 < nh && (j1 == j || cols + hlens[j1] + (uint32_t)(kc->G - 1) <= hs_cols) && (j1 - j) < 0xffff) {
+          while (j1 < nh && (j1 == j || cols + hlens[j1] + (uint32_t)(kc->G - 1) <= cols_limit) && (j1 - j) < 0xffff) {
             cols += hlens[j1] + (kc->G - 1);
             stage += round_up16(hlens[j1]);
             ++j1;

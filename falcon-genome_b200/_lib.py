@@ -77,6 +77,9 @@ SIGNATURES = {
     "fcs_pairhmm_batch_cells": (C.c_int64, [C.c_void_p]),
     "fcs_pairhmm_batch_launches": (C.c_int32, [C.c_void_p]),
     "fcs_pairhmm_batch_destroy": (None, [C.c_void_p, C.c_void_p]),
+    "fcs_pairhmm_set_capture": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "fcs_pairhmm_capture_load": (C.c_int, [C.c_char_p, C.POINTER(FlatStruct), C.POINTER(C.c_void_p)]),
+    "fcs_pairhmm_capture_free": (None, [C.c_void_p]),
     "fcs_pairhmm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "fcs_pairhmm_reset_stats": (C.c_int, [C.c_void_p]),
     "fcs_pairhmm_lut_ph2pr_f32": (C.c_float, [C.c_int]),

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <new>
 
+#include "phmm_capture.h"
 #include "phmm_engine.h"
 #include "phmm_luts.h"
 
@@ -219,6 +220,28 @@ int fcs_pairhmm_reset_stats(fcs_phmm_handle* h) {
   h->e->reset_stats();
   return FCS_PHMM_OK;
 }
+
+int fcs_pairhmm_set_capture(fcs_phmm_handle* h, const char* path) {
+  if (!h) return set_error(FCS_PHMM_EINVAL, "null handle");
+  API_TRY
+  return h->e->set_capture(path);
+  API_CATCH
+}
+
+int fcs_pairhmm_capture_load(const char* path, fcs_phmm_flat_batch* out, void** owner) {
+  if (!path || !out || !owner) return set_error(FCS_PHMM_EINVAL, "null argument");
+  *owner = nullptr;
+  API_TRY
+  LoadedCapture* c = nullptr;
+  int rc = load_capture(path, &c);
+  if (rc != FCS_PHMM_OK) return rc;
+  c->view(out);
+  *owner = c;
+  return FCS_PHMM_OK;
+  API_CATCH
+}
+
+void fcs_pairhmm_capture_free(void* owner) { delete static_cast<LoadedCapture*>(owner); }
 
 float fcs_pairhmm_lut_ph2pr_f32(int q) { return luts().ph2pr_f[q & 127]; }
 double fcs_pairhmm_lut_ph2pr_f64(int q) { return luts().ph2pr_d[q & 127]; }

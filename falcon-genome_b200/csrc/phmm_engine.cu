@@ -20,6 +20,7 @@
 #include <cstring>
 #include <numeric>
 
+#include "phmm_capture.h"
 #include "phmm_luts.h"
 
 namespace fcsphmm {
@@ -88,6 +89,20 @@ int ChunkPlan::launches() const {
 }
 
 // ---------------------------------------------------------------------------------------
+Engine::Engine() {}
+
+int Engine::set_capture(const char* path) {
+  if (!path || !*path) {
+    capture_.reset();
+    return FCS_PHMM_OK;
+  }
+  std::unique_ptr<CaptureWriter> w(new CaptureWriter());
+  int rc = w->open(path);
+  if (rc != FCS_PHMM_OK) return rc;
+  capture_ = std::move(w);
+  return FCS_PHMM_OK;
+}
+
 int Engine::create(const fcs_phmm_config* cfg, Engine** out) {
   *out = nullptr;
   std::unique_ptr<Engine> e(new Engine());
@@ -109,6 +124,10 @@ int Engine::init(const fcs_phmm_config* cfg) {
   max_chunk_cells_ = c.max_chunk_cells > 0 ? c.max_chunk_cells : env_i64("FCS_PHMM_CHUNK_CELLS", 0);  // 0 = adaptive
   // two slots per packing thread: a thread packs into one while its previous chunk is on the device
   int nslots = std::max(c.slots_per_device > 0 ? c.slots_per_device : 0, 2 * pack_threads_);
+  if (const char* cap = std::getenv("FCS_PHMM_CAPTURE")) {
+    int rc = set_capture(cap);
+    if (rc != FCS_PHMM_OK) return rc;
+  }
 
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -943,6 +962,10 @@ int Engine::compute(const Input& in) {
   const int64_t n = in.n_regions();
   if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
   if (n == 0) return FCS_PHMM_OK;
+  if (capture_ && capture_->active()) {
+    int rc = capture_->append(in);
+    if (rc != FCS_PHMM_OK) return rc;
+  }
   const size_t D = devs_.size();
   if (D == 1) {
     std::vector<int64_t> regs((size_t)n);

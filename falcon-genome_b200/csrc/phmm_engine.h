@@ -134,6 +134,7 @@ struct Stats {
 };
 
 struct Batch;  // device-resident batch
+class CaptureWriter;
 
 class Engine {
  public:
@@ -150,9 +151,10 @@ class Engine {
   int get_stats(fcs_phmm_stats* s);
   void reset_stats();
   int device_count() const { return (int)devs_.size(); }
+  int set_capture(const char* path);  // nullptr / empty = stop capturing
 
  private:
-  Engine() {}
+  Engine();
   int init(const fcs_phmm_config* cfg);
   int run_device(Device& d, const Input& in, const std::vector<int64_t>& regions);
   int pack_chunk(Slot& s, const Input& in);
@@ -175,6 +177,7 @@ class Engine {
   };
   std::map<fcs_phmm_ticket, std::unique_ptr<Pending>> tickets_;
   fcs_phmm_ticket next_ticket_ = 1;
+  std::unique_ptr<CaptureWriter> capture_;
   friend struct Batch;
 };
 

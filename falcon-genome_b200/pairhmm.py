@@ -231,6 +231,10 @@ class PairHMM:
     def resident(self, b: FlatBatch, device_index: int = 0) -> ResidentBatch:
         return ResidentBatch(self, b, device_index)
 
+    def set_capture(self, path: Optional[str]):
+        """Append every region scored from now on to `path` (FCSPHMM1 format); None stops."""
+        self._check(self._lib.fcs_pairhmm_set_capture(self._h, path.encode() if path else None))
+
     # -- introspection ------------------------------------------------------------------
     def stats(self) -> dict:
         s = _lib.Stats()

@@ -186,6 +186,16 @@ FCS_PHMM_API int64_t fcs_pairhmm_batch_cells(const fcs_phmm_batch* b);
 FCS_PHMM_API int32_t fcs_pairhmm_batch_launches(const fcs_phmm_batch* b); /* kernels one batch_run enqueues */
 FCS_PHMM_API void fcs_pairhmm_batch_destroy(fcs_phmm_handle* h, fcs_phmm_batch* b);
 
+/* ---- capture / replay of testcases at this boundary -----------------
+ * set_capture: append every region passed to compute / compute_flat / submit to `path` (format in
+ * falcon-genome_b200/csrc/phmm_capture.h); NULL or "" stops.  The environment variable
+ * FCS_PHMM_CAPTURE=<path> enables it at create time (e.g. under a JVM through the JNI shim).
+ * capture_load: read such a file into a flat batch that points into `*owner`; free with capture_free.
+ * Both are host-only (no device needed). */
+FCS_PHMM_API int fcs_pairhmm_set_capture(fcs_phmm_handle* h, const char* path);
+FCS_PHMM_API int fcs_pairhmm_capture_load(const char* path, fcs_phmm_flat_batch* out, void** owner);
+FCS_PHMM_API void fcs_pairhmm_capture_free(void* owner);
+
 /* ---- introspection ------------------------------------------------------------------ */
 FCS_PHMM_API int fcs_pairhmm_get_stats(fcs_phmm_handle* h, fcs_phmm_stats* out);
 FCS_PHMM_API int fcs_pairhmm_reset_stats(fcs_phmm_handle* h);

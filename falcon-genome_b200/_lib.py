@@ -42,6 +42,11 @@ class Config(C.Structure):
                 ("keep_raw_f32", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PrepParams(C.Structure):
+    _fields_ = [("base_q_threshold", C.c_int32), ("min_usable_q", C.c_int32), ("default_indel_q", C.c_int32), ("gcp", C.c_int32),
+                ("pcr_model", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("cells", C.c_uint64), ("fp64_pairs", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("chunks", C.c_uint64), ("kernel_ms", C.c_double),
@@ -80,6 +85,8 @@ SIGNATURES = {
     "fcs_pairhmm_set_capture": (C.c_int, [C.c_void_p, C.c_char_p]),
     "fcs_pairhmm_capture_load": (C.c_int, [C.c_char_p, C.POINTER(FlatStruct), C.POINTER(C.c_void_p)]),
     "fcs_pairhmm_capture_free": (None, [C.c_void_p]),
+    "fcs_pairhmm_prepare_read": (C.c_int, [u8p, u8p, C.c_int32, C.c_int32, u8p, u8p, C.POINTER(PrepParams), u8p, u8p, u8p, u8p]),
+    "fcs_pairhmm_finalize_region": (C.c_int, [f64p, C.c_int32, C.c_int32, i32p, C.c_double, C.c_double, u8p]),
     "fcs_pairhmm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "fcs_pairhmm_reset_stats": (C.c_int, [C.c_void_p]),
     "fcs_pairhmm_lut_ph2pr_f32": (C.c_float, [C.c_int]),

@@ -243,6 +243,22 @@ int fcs_pairhmm_capture_load(const char* path, fcs_phmm_flat_batch* out, void** 
 
 void fcs_pairhmm_capture_free(void* owner) { delete static_cast<LoadedCapture*>(owner); }
 
+int fcs_pairhmm_prepare_read(const uint8_t* bases, const uint8_t* raw_base_q, int32_t len, int32_t mapq, const uint8_t* bam_ins_q,
+                             const uint8_t* bam_del_q, const fcs_phmm_prep_params* params, uint8_t* out_base_q, uint8_t* out_ins_q,
+                             uint8_t* out_del_q, uint8_t* out_gcp) {
+  API_TRY
+  return prepare_read(bases, raw_base_q, len, mapq, bam_ins_q, bam_del_q, params, out_base_q, out_ins_q, out_del_q, out_gcp);
+  API_CATCH
+}
+
+int fcs_pairhmm_finalize_region(double* log10_likelihoods, int32_t n_reads, int32_t n_haps, const int32_t* read_len,
+                                double log10_global_mismapping_rate, double expected_error_rate_per_base, uint8_t* out_poorly_modeled) {
+  API_TRY
+  return finalize_region(log10_likelihoods, n_reads, n_haps, read_len, log10_global_mismapping_rate, expected_error_rate_per_base,
+                         out_poorly_modeled);
+  API_CATCH
+}
+
 float fcs_pairhmm_lut_ph2pr_f32(int q) { return luts().ph2pr_f[q & 127]; }
 double fcs_pairhmm_lut_ph2pr_f64(int q) { return luts().ph2pr_d[q & 127]; }
 float fcs_pairhmm_lut_mm_f32(int i, int d) { return luts().mm_f[mm_index(i & 127, d & 127)]; }

@@ -189,6 +189,10 @@ struct Batch {
   std::vector<uint64_t> reg_pairs;  // pairs per planned region
 };
 
+int prepare_read(const uint8_t* bases, const uint8_t* raw_q, int32_t len, int32_t mapq, const uint8_t* bam_ins, const uint8_t* bam_del,
+                 const fcs_phmm_prep_params* pp, uint8_t* out_q, uint8_t* out_i, uint8_t* out_d, uint8_t* out_c);
+int finalize_region(double* l, int32_t n_reads, int32_t n_haps, const int32_t* read_len, double log10_mismap, double err_rate, uint8_t* poorly);
+
 std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw);
 
 }  // namespace fcsphmm

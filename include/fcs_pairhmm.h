@@ -196,6 +196,24 @@ FCS_PHMM_API int fcs_pairhmm_set_capture(fcs_phmm_handle* h, const char* path);
 FCS_PHMM_API int fcs_pairhmm_capture_load(const char* path, fcs_phmm_flat_batch* out, void** owner);
 FCS_PHMM_API void fcs_pairhmm_capture_free(void* owner);
 
+/* ---- GATK-side steps either side of the kernel (host-only) -------------
+ * [upstream GATK4 PairHMMLikelihoodCalculationEngine, restated]  prepare_read turns a raw read into the
+ * four qual arrays the kernel takes: base quals capped by mapq (mapq < 0 = no cap), then
+ * q < base_q_threshold -> min_usable_q; ins/del quals from the BAM tags or default_indel_q, lowered by
+ * the PCR indel model (0 none, 1 hostile, 2 aggressive, 3 conservative) inside tandem repeats;
+ * gcp constant.  params == NULL: {18, 6, 45, 10, 3}.  finalize_region caps every read's row at
+ * best + log10_global_mismapping_rate (GATK: -4.5) and flags reads whose best likelihood is below
+ * min(2, ceil(len * expected_error_rate_per_base (0.02))) * -4.0. */
+typedef struct {
+  int32_t base_q_threshold, min_usable_q, default_indel_q, gcp, pcr_model;
+} fcs_phmm_prep_params;
+FCS_PHMM_API int fcs_pairhmm_prepare_read(const uint8_t* bases, const uint8_t* raw_base_q, int32_t len, int32_t mapq,
+                                          const uint8_t* bam_ins_q, const uint8_t* bam_del_q, const fcs_phmm_prep_params* params,
+                                          uint8_t* out_base_q, uint8_t* out_ins_q, uint8_t* out_del_q, uint8_t* out_gcp);
+FCS_PHMM_API int fcs_pairhmm_finalize_region(double* log10_likelihoods, int32_t n_reads, int32_t n_haps, const int32_t* read_len,
+                                             double log10_global_mismapping_rate, double expected_error_rate_per_base,
+                                             uint8_t* out_poorly_modeled);
+
 /* ---- introspection ------------------------------------------------------------------ */
 FCS_PHMM_API int fcs_pairhmm_get_stats(fcs_phmm_handle* h, fcs_phmm_stats* out);
 FCS_PHMM_API int fcs_pairhmm_reset_stats(fcs_phmm_handle* h);

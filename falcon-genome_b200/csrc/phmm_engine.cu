@@ -169,6 +169,7 @@ int Engine::init(const fcs_phmm_config* cfg) {
     for (Slot& s : d->slots) CK(init_slot(s));
     devs_.push_back(std::move(d));
   }
+  pool_.reset(new WorkerPool(std::max(0, (int)devs_.size() * pack_threads_ - 1)));
   return FCS_PHMM_OK;
 }
 
@@ -212,6 +213,7 @@ Engine::~Engine() {
       if (kv.second->th.joinable()) kv.second->th.join();
     tickets_.clear();
   }
+  pool_.reset();
   for (auto& d : devs_) {
     cudaSetDevice(d->ordinal);
     for (Slot& s : d->slots) free_slot(s);
@@ -849,43 +851,132 @@ int Engine::retire_slot(Device& d, Slot& s) {
   return FCS_PHMM_OK;
 }
 
-// One device: cut the device's regions into chunks, then let `pack_threads_` host threads each
-// plan + pack + launch whole chunks on their own pair of slots (GATK's --native-pair-hmm-threads,
-// /root/reference/src/workers/HTCWorker.cpp:85, maps onto this count).  Packing chunk k+1 overlaps
-// the device work of chunk k, and chunks of different threads overlap on the device.
-int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& regions) {
-  std::lock_guard<std::mutex> lk(d.mu);
-  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
-  // ---- chunk boundaries (cells, pairs and byte limits).  Unless the caller fixed a chunk size, aim
-  // at about two chunks per packing thread: enough to pipeline host packing against the device,
-  // few enough that each kernel launch still has a device-filling number of tasks.
-  std::vector<std::vector<int64_t>> chunks;
+// ---------------------------------------------------------------------------------------
+WorkerPool::WorkerPool(int n_threads) {
+  for (int i = 0; i < n_threads; ++i) th_.emplace_back([this] { loop(); });
+}
+WorkerPool::~WorkerPool() {
   {
-    std::vector<uint64_t> rc_cells(regions.size()), rc_pairs(regions.size()), rc_bytes(regions.size());
-    uint64_t total = 0;
-    for (size_t k = 0; k < regions.size(); ++k) {
-      const int64_t g = regions[k];
-      int32_t nr = 0, nh = 0;
-      in.shape(g, nr, nh);
-      uint64_t sr = 0, sh = 0;
-      for (int32_t i = 0; i < nr; ++i) sr += (uint64_t)std::max(0, in.read(g, i).len);
-      for (int32_t j = 0; j < nh; ++j) sh += (uint64_t)std::max(0, in.hap(g, j).len);
-      rc_cells[k] = sr * sh;
-      rc_pairs[k] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
-      rc_bytes[k] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
-      total += rc_cells[k];
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  for (auto& t : th_) t.join();
+}
+void WorkerPool::drain() {
+  for (;;) {
+    const int j = next_.fetch_add(1);
+    if (j >= n_jobs_) break;
+    (*fn_)(j);
+    std::lock_guard<std::mutex> lk(mu_);
+    if (--pending_ == 0) done_cv_.notify_all();
+  }
+}
+void WorkerPool::loop() {
+  uint64_t seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+      if (stop_) return;
+      seen = gen_;
     }
+    drain();
+  }
+}
+void WorkerPool::run(int n_jobs, const std::function<void(int)>& fn) {
+  if (n_jobs <= 0) return;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    fn_ = &fn;
+    n_jobs_ = n_jobs;
+    pending_ = n_jobs;
+    next_.store(0);
+    ++gen_;
+  }
+  cv_.notify_all();
+  drain();  // the caller works too
+  std::unique_lock<std::mutex> lk(mu_);
+  done_cv_.wait(lk, [&] { return pending_ == 0; });
+  n_jobs_ = 0;  // late wakers find nothing to do
+}
+
+// One call: a single pass sizes every region; regions are split over the devices by DP cells
+// (longest-processing-time-first: independent regions, no exchange -- the reference fans out one
+// process per genome partition the same way, /root/reference/src/worker-htc.cpp:113-145); each device's
+// share is cut into chunks; `pack_threads_` persistent host threads per device (GATK's
+// --native-pair-hmm-threads, src/workers/HTCWorker.cpp:85) each plan + pack + launch whole chunks on
+// their own pair of slots, so packing chunk k+1 overlaps the device work of chunk k and chunks of
+// different threads overlap on the device.
+int Engine::compute(const Input& in) {
+  const int64_t n = in.n_regions();
+  if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
+  if (n == 0) return FCS_PHMM_OK;
+  std::lock_guard<std::mutex> call_lock(compute_mu_);
+  if (capture_ && capture_->active()) {
+    int rc = capture_->append(in);
+    if (rc != FCS_PHMM_OK) return rc;
+  }
+  const size_t D = devs_.size();
+  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
+  // ---- size every region once
+  std::vector<uint64_t> rc_cells((size_t)n), rc_pairs((size_t)n), rc_bytes((size_t)n);
+  for (int64_t g = 0; g < n; ++g) {
+    int32_t nr = 0, nh = 0;
+    in.shape(g, nr, nh);
+    uint64_t sr = 0, sh = 0;
+    for (int32_t i = 0; i < nr; ++i) sr += (uint64_t)std::max(0, in.read(g, i).len);
+    for (int32_t j = 0; j < nh; ++j) sh += (uint64_t)std::max(0, in.hap(g, j).len);
+    rc_cells[(size_t)g] = sr * sh;
+    rc_pairs[(size_t)g] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
+    rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
+  }
+  // ---- regions -> devices
+  std::vector<std::vector<int64_t>> part(D);
+  if (D == 1) {
+    part[0].resize((size_t)n);
+    std::iota(part[0].begin(), part[0].end(), (int64_t)0);
+  } else {
+    std::vector<int64_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      return rc_cells[(size_t)a] > rc_cells[(size_t)b] || (rc_cells[(size_t)a] == rc_cells[(size_t)b] && a < b); });
+    std::vector<uint64_t> load(D, 0);
+    for (int64_t g : order) {
+      size_t best = 0;
+      for (size_t d = 1; d < D; ++d)
+        if (load[d] < load[best]) best = d;
+      part[best].push_back(g);
+      load[best] += rc_cells[(size_t)g];
+    }
+    for (auto& p : part) std::sort(p.begin(), p.end());
+  }
+  // ---- per device: chunk boundaries (cells, pairs and byte limits).  Unless the caller fixed a chunk
+  // size, aim at about two chunks per packing thread: enough to pipeline host packing against the
+  // device, few enough that each launch still has a device-filling number of tasks.  The first chunk
+  // of every packing thread is a quarter of the regular size so that the device starts early.
+  struct DevWork {
+    std::vector<std::vector<int64_t>> chunks;
+    std::atomic<size_t> next{0};
+    int threads = 0;
+  };
+  std::vector<DevWork> work(D);
+  int n_jobs = 0;
+  std::vector<std::pair<int, int>> jobs;  // (device, worker)
+  for (size_t d = 0; d < D; ++d) {
+    uint64_t total = 0;
+    for (int64_t g : part[d]) total += rc_cells[(size_t)g];
     int64_t limit = max_chunk_cells_;
+    const bool ramp = limit <= 0;
     if (limit <= 0) {
       const int64_t want = (int64_t)(total / (uint64_t)(2 * std::max(1, pack_threads_)));
       limit = std::min<int64_t>(8000000000LL, std::max<int64_t>(500000000LL, want));
     }
     uint64_t cells = 0, pairs = 0, bytes = 0;
     std::vector<int64_t> cur;
-    // ramp: the first chunk of every packing thread is a quarter of the regular size, so the device
-    // starts early instead of idling while the host packs a full-size first chunk
-    const bool ramp = max_chunk_cells_ <= 0;
-    for (size_t k = 0; k < regions.size(); ++k) {
+    auto& chunks = work[d].chunks;
+    for (int64_t g : part[d]) {
+      const size_t k = (size_t)g;
       const int64_t lim_now = (ramp && (int)chunks.size() < pack_threads_) ? std::max<int64_t>(limit / 4, 125000000LL) : limit;
       if (!cur.empty() && cells > 0 &&
           ((int64_t)(cells + rc_cells[k]) > lim_now || pairs + rc_pairs[k] > 0x7fffffffULL || bytes + rc_bytes[k] > (1ull << 31))) {
@@ -893,13 +984,14 @@ int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& r
         cur.clear();
         cells = pairs = bytes = 0;
       }
-      cur.push_back(regions[k]);
+      cur.push_back(g);
       cells += rc_cells[k]; pairs += rc_pairs[k]; bytes += rc_bytes[k];
     }
     if (!cur.empty()) chunks.emplace_back(std::move(cur));
+    work[d].threads = (int)std::min<size_t>({(size_t)pack_threads_, chunks.size(), devs_[d]->slots.size() / 2});
+    for (int w = 0; w < work[d].threads; ++w) jobs.emplace_back((int)d, w);
+    n_jobs += work[d].threads;
   }
-  const int T = (int)std::max<size_t>(1, std::min<size_t>({(size_t)pack_threads_, chunks.size(), d.slots.size() / 2}));
-  std::atomic<size_t> next_chunk{0};
   std::atomic<int> first_rc{FCS_PHMM_OK};
   std::mutex err_mu;
   std::string err_text;
@@ -910,20 +1002,23 @@ int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& r
       err_text = last_error();
     }
   };
-  auto worker = [&](int w) {
+  const std::function<void(int)> worker = [&](int job) {
+    Device& d = *devs_[(size_t)jobs[(size_t)job].first];
+    DevWork& dw = work[(size_t)jobs[(size_t)job].first];
+    const int w = jobs[(size_t)job].second;
     if (cudaSetDevice(d.ordinal) != cudaSuccess) { set_error(FCS_PHMM_ECUDA, "cudaSetDevice failed"); fail_with(FCS_PHMM_ECUDA); return; }
     int use = 0;
     while (first_rc.load() == FCS_PHMM_OK) {
-      const size_t c = next_chunk.fetch_add(1);
-      if (c >= chunks.size()) break;
+      const size_t c = dw.next.fetch_add(1);
+      if (c >= dw.chunks.size()) break;
       Slot& s = d.slots[(size_t)2 * w + (size_t)(use++ & 1)];
       int rc = retire_slot(d, s);
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
       const double t0 = now_ms();
       size_t next = 0;
       Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count};
-      rc = pl.run(chunks[c], 0, next);
-      if (rc == FCS_PHMM_OK && next != chunks[c].size()) rc = set_error(FCS_PHMM_EUNSUPPORTED, "a single region exceeds the chunk limits (2^31 pairs / 2 GiB)");
+      rc = pl.run(dw.chunks[c], 0, next);
+      if (rc == FCS_PHMM_OK && next != dw.chunks[c].size()) rc = set_error(FCS_PHMM_EUNSUPPORTED, "a single region exceeds the chunk limits (2^31 pairs / 2 GiB)");
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
       if (s.plan.n_pairs == 0) continue;
       rc = ensure_buffers(s, s.plan.in_bytes, s.plan.total_bytes - s.plan.off_out, s.plan.total_bytes);
@@ -946,65 +1041,9 @@ int Engine::run_device(Device& d, const Input& in, const std::vector<int64_t>& r
       if (r2 != FCS_PHMM_OK) fail_with(r2);
     }
   };
-  if (T == 1) {
-    worker(0);
-  } else {
-    std::vector<std::thread> th;
-    for (int w = 1; w < T; ++w) th.emplace_back(worker, w);
-    worker(0);
-    for (auto& t : th) t.join();
-  }
+  if (n_jobs == 1) worker(0);
+  else pool_->run(n_jobs, worker);
   if (first_rc.load() != FCS_PHMM_OK) return set_error(first_rc.load(), err_text);
-  return FCS_PHMM_OK;
-}
-
-int Engine::compute(const Input& in) {
-  const int64_t n = in.n_regions();
-  if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
-  if (n == 0) return FCS_PHMM_OK;
-  if (capture_ && capture_->active()) {
-    int rc = capture_->append(in);
-    if (rc != FCS_PHMM_OK) return rc;
-  }
-  const size_t D = devs_.size();
-  if (D == 1) {
-    std::vector<int64_t> regs((size_t)n);
-    std::iota(regs.begin(), regs.end(), (int64_t)0);
-    return run_device(*devs_[0], in, regs);
-  }
-  // longest-processing-time-first partition of regions over the devices by DP cells
-  std::vector<std::pair<uint64_t, int64_t>> cost((size_t)n);
-  for (int64_t g = 0; g < n; ++g) {
-    int32_t nr = 0, nh = 0;
-    in.shape(g, nr, nh);
-    uint64_t sr = 0, sh = 0;
-    for (int32_t i = 0; i < nr; ++i) sr += (uint64_t)std::max(0, in.read(g, i).len);
-    for (int32_t j = 0; j < nh; ++j) sh += (uint64_t)std::max(0, in.hap(g, j).len);
-    cost[(size_t)g] = {sr * sh, g};
-  }
-  std::sort(cost.begin(), cost.end(), [](const auto& a, const auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
-  std::vector<std::vector<int64_t>> part(D);
-  std::vector<uint64_t> load(D, 0);
-  for (const auto& c : cost) {
-    size_t best = 0;
-    for (size_t d = 1; d < D; ++d)
-      if (load[d] < load[best]) best = d;
-    part[best].push_back(c.second);
-    load[best] += c.first;
-  }
-  for (auto& p : part) std::sort(p.begin(), p.end());
-  std::vector<int> rcs(D, FCS_PHMM_OK);
-  std::vector<std::string> errs(D);
-  std::vector<std::thread> th;
-  for (size_t d = 0; d < D; ++d) {
-    th.emplace_back([&, d] {
-      rcs[d] = run_device(*devs_[d], in, part[d]);
-      if (rcs[d] != FCS_PHMM_OK) errs[d] = last_error();
-    });
-  }
-  for (auto& t : th) t.join();
-  for (size_t d = 0; d < D; ++d)
-    if (rcs[d] != FCS_PHMM_OK) return set_error(rcs[d], errs[d]);
   return FCS_PHMM_OK;
 }
 

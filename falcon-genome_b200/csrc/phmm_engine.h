@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -133,6 +134,26 @@ struct Stats {
   double plan_ms = 0, pack_ms = 0, wait_ms = 0, scatter_ms = 0;  // host-side phases of compute()
 };
 
+// Persistent host threads: run(n, fn) executes fn(0..n-1) on the pool plus the calling thread.
+class WorkerPool {
+ public:
+  explicit WorkerPool(int n_threads);
+  ~WorkerPool();
+  void run(int n_jobs, const std::function<void(int)>& fn);
+
+ private:
+  void loop();
+  void drain();
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int n_jobs_ = 0, pending_ = 0;
+  std::atomic<int> next_{0};
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 struct Batch;  // device-resident batch
 class CaptureWriter;
 
@@ -156,7 +177,6 @@ class Engine {
  private:
   Engine();
   int init(const fcs_phmm_config* cfg);
-  int run_device(Device& d, const Input& in, const std::vector<int64_t>& regions);
   int pack_chunk(Slot& s, const Input& in);
   int launch_chunk(Device& d, Slot& s, bool upload, bool download);
   int retire_slot(Device& d, Slot& s);
@@ -178,6 +198,8 @@ class Engine {
   std::map<fcs_phmm_ticket, std::unique_ptr<Pending>> tickets_;
   fcs_phmm_ticket next_ticket_ = 1;
   std::unique_ptr<CaptureWriter> capture_;
+  std::unique_ptr<WorkerPool> pool_;
+  std::mutex compute_mu_;  // one compute() at a time drives the slots and the pool
   friend struct Batch;
 };
 

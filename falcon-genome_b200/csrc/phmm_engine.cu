@@ -279,6 +279,24 @@ struct Planner {
     s.genlist.clear();
     s.gen_flags.clear();
     uint32_t gen64_cap = 0, gen_maxlh = 0;
+    // Latency policy for under-filled chunks: if even with one task per (4 reads x 1 haplotype) the chunk
+    // cannot fill the one-warp CTA slots of the device, the call is latency bound: the time is the serial
+    // chain of one task.  Then give every read the widest lane group (shortest chain per column) that still
+    // yields enough tasks, and one haplotype per task.
+    int min_G = 0;
+    {
+      uint64_t reads_x_haps = 0;
+      for (size_t kk = first; kk < regions.size(); ++kk) {
+        int32_t nr = 0, nh = 0;
+        in.shape(regions[kk], nr, nh);
+        reads_x_haps += (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
+        if (reads_x_haps > (uint64_t)sm_count * 64) break;
+      }
+      // tasks = reads_x_haps / (32 / G) must fit one wave of CTAs, else the throughput policy is better
+      const uint64_t slots = (uint64_t)sm_count * 10;
+      if (reads_x_haps <= slots) min_G = 32;
+      else if (reads_x_haps / 2 <= slots) min_G = 16;
+    }
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps;
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
@@ -340,7 +358,8 @@ struct Planner {
       // columns.  Tasks are launched longest first, so the short ones fill the end of the grid and
       // the last wave of CTAs is half as long (equal-size tasks finish in lock step otherwise).
       static const int tail_pct = (int)env_i64("FCS_PHMM_TAIL_PCT", 25);
-      const uint32_t cols_limit = (k - first) * 100 >= (regions.size() - first) * (size_t)(100 - tail_pct) ? std::max(hs_cols / 2, 1u) : hs_cols;
+      const uint32_t cols_limit =
+          min_G ? 1u : ((k - first) * 100 >= (regions.size() - first) * (size_t)(100 - tail_pct) ? std::max(hs_cols / 2, 1u) : hs_cols);
       const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
       uint32_t maxlh = 0;
       for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
@@ -359,7 +378,8 @@ struct Planner {
         // full groups of the longest remaining read use the table; the last, partly filled group of a
         // region asks for the class that is cheapest per read actually served
         const ClassRef* k0 = f32_class_of_len(false, (int)lens[ord[i]]);
-        if (nr - i < 32 / k0->G) k0 = select_class_for(false, false, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
+        if (min_G) k0 = select_class_wide(false, false, (int)lens[ord[i]], min_G);
+        else if (nr - i < 32 / k0->G) k0 = select_class_for(false, false, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
         const int NG = 32 / k0->G;
         const int cnt = std::min<int32_t>(NG, nr - i);
         int tg = gcps[ord[i]];  // uniform-GCP form only if every read of the task shares the value
@@ -401,7 +421,11 @@ struct Planner {
       // ---- FP64 queue capacity per class (worst case: every pair of the read falls back)
       for (int32_t i = 0; i < nr; ++i) {
         if (long_hap || lens[i] > (uint32_t)kGenericMaxSinglePassRead) continue;  // counted in gen64_cap
-        const int c64 = qid_of_len((int)lens[i]);
+        int c64 = qid_of_len((int)lens[i]);
+        if (min_G) {
+          const ClassRef* kw = select_class_wide(true, false, (int)lens[i], 32);
+          c64 = f64_queue_id(kw->G, kw->R);
+        }
         f64_cap[c64] += (uint32_t)nh;
         f64_maxlh[c64] = std::max(f64_maxlh[c64], maxlh);
         chunk_gcp = (chunk_gcp == -2) ? gcps[i] : (chunk_gcp == gcps[i] ? chunk_gcp : -1);
@@ -419,6 +443,7 @@ struct Planner {
     next = k;
     // ---- layout
     size_t off = 0;
+    P.latency_mode = min_G != 0;
     P.off_reads = off; off = align_up(off + reads_bytes, 256);
     P.off_haps = off; off = align_up(off + haps_bytes, 256);
     P.off_rmeta = off; off = align_up(off + P.n_reads * sizeof(ReadMeta), 256);
@@ -610,7 +635,11 @@ int Engine::pack_chunk(Slot& s, const Input& in) {
         std::memcpy(dst + (size_t)pl * lp, src[pl], (size_t)r.len);
         std::memset(dst + (size_t)pl * lp + r.len, 0, lp - (uint32_t)r.len);
       }
-      const int c64 = s.gen_flags[ridx] ? kQueueGenericF64 : qid_of_len(r.len);
+      int c64 = s.gen_flags[ridx] ? kQueueGenericF64 : qid_of_len(r.len);
+      if (P.latency_mode && !s.gen_flags[ridx]) {
+        const ClassRef* kw = select_class_wide(true, false, r.len, 32);
+        c64 = f64_queue_id(kw->G, kw->R);
+      }
       ReadMeta& m = rmeta[ridx];
       m.data_off16 = (uint32_t)(rpos / 16);
       m.len_cls = (uint32_t)r.len | ((uint32_t)c64 << 24);

@@ -88,6 +88,7 @@ struct ChunkPlan {
   std::vector<F64Range> f64;
   std::vector<F64Queue> queues;
   bool force_double = false;
+  bool latency_mode = false;  // under-filled chunk: widest lane groups, one haplotype per task
   int f64_gcp = -1;  // >= 0: every read of the chunk shares this gap-continuation quality
   int launches() const;
 };

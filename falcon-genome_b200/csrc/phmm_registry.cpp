@@ -82,6 +82,18 @@ const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, i
   return best;
 }
 
+const ClassRef* select_class_wide(bool f64, bool ug, int read_len, int min_G) {
+  std::call_once(g_once, build);
+  if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
+  const ClassRef* best = nullptr;
+  for (const ClassRef& k : g_classes[(f64 ? 2 : 0) + (ug ? 1 : 0)]) {
+    if (k.G * k.R < read_len + 1 || k.G < min_G) continue;
+    // fewest rows per lane first (shortest dependent chain per step), then fewest lanes
+    if (!best || k.R < best->R || (k.R == best->R && k.G < best->G)) best = &k;
+  }
+  return best ? best : select_class(f64, ug, read_len);
+}
+
 const ClassRef* find_class(bool f64, bool ug, int G, int R) {
   std::call_once(g_once, build);
   for (const ClassRef& k : g_classes[(f64 ? 2 : 0) + (ug ? 1 : 0)])

@@ -41,6 +41,9 @@ const ClassRef* select_class(bool f64, bool ug, int read_len);
 // against haplotypes of about avg_hap_len columns: favours wide groups (large G, small R) for leftovers.
 const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, int avg_hap_len);
 const ClassRef* find_class(bool f64, bool ug, int G, int R);
+// Latency policy (under-filled calls): the class with at least min_G lanes per read and the fewest rows
+// per lane that covers the read -- the shortest serial chain per haplotype column.
+const ClassRef* select_class_wide(bool f64, bool ug, int read_len, int min_G);
 // FP64 rerun queues are keyed by the (G, R) of the general-form FP64 class of the read.
 int f64_queue_count();
 int f64_queue_id(int G, int R);

@@ -260,3 +260,34 @@ def test_in_process_multi_gpu_dispatch(oracle):
         on, un = hn.compute_flat(b)
         assert hn.stats()["chunks"] >= 2
     assert np.array_equal(o1, on) and np.array_equal(u1, un)
+
+
+def test_concurrent_callers_on_one_handle(hmm):
+    """GATK drives the native library from several threads (--native-pair-hmm-threads,
+    /root/reference/src/workers/HTCWorker.cpp:85): concurrent compute() calls on one handle must be
+    safe and give the single-threaded results (ctypes releases the GIL during the call)."""
+    import threading
+
+    batches = [synth.tiny_mixed(seed=50 + i, n_regions=5) for i in range(6)] + [synth.config1_golden(n_regions=6, seed=60)]
+    ref = [hmm.compute_flat(b)[0] for b in batches]
+    errs = []
+
+    def work(tid):
+        try:
+            for rep in range(4):
+                for k, b in enumerate(batches):
+                    if (k + rep + tid) % 2 == 0:
+                        out, _ = hmm.compute_flat(b)
+                    else:
+                        out, _ = hmm.compute_regions(b)
+                    if not np.array_equal(out, ref[k]):
+                        errs.append((tid, rep, k))
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs[:3]

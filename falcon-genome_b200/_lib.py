@@ -84,6 +84,7 @@ SIGNATURES = {
     "fcs_pairhmm_batch_destroy": (None, [C.c_void_p, C.c_void_p]),
     "fcs_pairhmm_set_capture": (C.c_int, [C.c_void_p, C.c_char_p]),
     "fcs_pairhmm_capture_load": (C.c_int, [C.c_char_p, C.POINTER(FlatStruct), C.POINTER(C.c_void_p)]),
+    "fcs_pairhmm_capture_parse": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(FlatStruct), C.POINTER(C.c_void_p)]),
     "fcs_pairhmm_capture_free": (None, [C.c_void_p]),
     "fcs_pairhmm_prepare_read": (C.c_int, [u8p, u8p, C.c_int32, C.c_int32, u8p, u8p, C.POINTER(PrepParams), u8p, u8p, u8p, u8p]),
     "fcs_pairhmm_finalize_region": (C.c_int, [f64p, C.c_int32, C.c_int32, i32p, C.c_double, C.c_double, u8p]),
@@ -96,7 +97,32 @@ SIGNATURES = {
     "fcs_pairhmm_kernel_class": (C.c_int, [C.c_int32, C.c_int32, i32p, i32p]),
 }
 
+# libfcs_pairhmm_client.so (no CUDA): client of the fcs-pairhmm-nam daemon
+CLIENT_LIB_PATH = os.path.join(_HERE, "libfcs_pairhmm_client.so")
+CLIENT_SIGNATURES = {
+    "fcs_pairhmm_remote_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "fcs_pairhmm_remote_compute_flat": (C.c_int, [C.c_void_p, C.POINTER(FlatStruct), f64p, u8p]),
+    "fcs_pairhmm_remote_last_error": (C.c_char_p, [C.c_void_p]),
+    "fcs_pairhmm_remote_close": (None, [C.c_void_p]),
+}
+
 _lib = None
+_client = None
+
+
+def load_client() -> C.CDLL:
+    global _client
+    if _client is None:
+        if not os.path.exists(CLIENT_LIB_PATH):
+            raise OSError(f"{CLIENT_LIB_PATH} is missing: build it with `python __graft_entry__.py build`")
+        lib = C.CDLL(CLIENT_LIB_PATH)
+        for name, (res, args) in CLIENT_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _client = lib
+    return _client
+
 
 
 def load() -> C.CDLL:

@@ -241,6 +241,18 @@ int fcs_pairhmm_capture_load(const char* path, fcs_phmm_flat_batch* out, void** 
   API_CATCH
 }
 
+int fcs_pairhmm_capture_parse(const void* blocks, uint64_t n_bytes, fcs_phmm_flat_batch* out, void** owner) {
+  if (!blocks || !out || !owner) return set_error(FCS_PHMM_EINVAL, "null argument");
+  *owner = nullptr;
+  API_TRY
+  std::unique_ptr<LoadedCapture> c(new LoadedCapture());
+  if (!parse_blocks(static_cast<const uint8_t*>(blocks), (size_t)n_bytes, *c)) return set_error(FCS_PHMM_EINVAL, "truncated or corrupt capture blocks");
+  c->view(out);
+  *owner = c.release();
+  return FCS_PHMM_OK;
+  API_CATCH
+}
+
 void fcs_pairhmm_capture_free(void* owner) { delete static_cast<LoadedCapture*>(owner); }
 
 int fcs_pairhmm_prepare_read(const uint8_t* bases, const uint8_t* raw_base_q, int32_t len, int32_t mapq, const uint8_t* bam_ins_q,

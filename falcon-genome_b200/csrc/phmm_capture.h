@@ -38,4 +38,9 @@ struct LoadedCapture {
 };
 int load_capture(const std::string& path, LoadedCapture** out);
 
+// One 'RBLK' block in memory (the broker protocol sends exactly this).
+void serialize_block(const Input& in, std::vector<uint8_t>& out);
+// Parses a sequence of blocks; appends to `c`.  Returns false on truncation / corruption.
+bool parse_blocks(const uint8_t* p, size_t n, LoadedCapture& c);
+
 }  // namespace fcsphmm

@@ -194,6 +194,8 @@ FCS_PHMM_API void fcs_pairhmm_batch_destroy(fcs_phmm_handle* h, fcs_phmm_batch* 
  * Both are host-only (no device needed). */
 FCS_PHMM_API int fcs_pairhmm_set_capture(fcs_phmm_handle* h, const char* path);
 FCS_PHMM_API int fcs_pairhmm_capture_load(const char* path, fcs_phmm_flat_batch* out, void** owner);
+/* Same, from capture blocks in memory (no file header): what the fcs-pairhmm-nam daemon receives. */
+FCS_PHMM_API int fcs_pairhmm_capture_parse(const void* blocks, uint64_t n_bytes, fcs_phmm_flat_batch* out, void** owner);
 FCS_PHMM_API void fcs_pairhmm_capture_free(void* owner);
 
 /* ---- GATK-side steps either side of the kernel (host-only) -------------
@@ -213,6 +215,16 @@ FCS_PHMM_API int fcs_pairhmm_prepare_read(const uint8_t* bases, const uint8_t* r
 FCS_PHMM_API int fcs_pairhmm_finalize_region(double* log10_likelihoods, int32_t n_reads, int32_t n_haps, const int32_t* read_len,
                                              double log10_global_mismapping_rate, double expected_error_rate_per_base,
                                              uint8_t* out_poorly_modeled);
+
+/* ---- service seam: client of the fcs-pairhmm-nam daemon -----------------
+ * The daemon (falcon-genome_b200/csrc/fcs_pairhmm_nam.cpp) owns the GPUs for the lifetime of a stage, as the
+ * Blaze NAM does in the reference (src/worker-htc.cpp:99-112, src/BackgroundExecutor.cpp:13-84).  These
+ * four symbols live in libfcs_pairhmm_client.so, which has no CUDA dependency. */
+typedef struct fcs_phmm_remote fcs_phmm_remote;
+FCS_PHMM_API int fcs_pairhmm_remote_open(const char* socket_path, fcs_phmm_remote** out);
+FCS_PHMM_API int fcs_pairhmm_remote_compute_flat(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64);
+FCS_PHMM_API const char* fcs_pairhmm_remote_last_error(const fcs_phmm_remote* r);
+FCS_PHMM_API void fcs_pairhmm_remote_close(fcs_phmm_remote* r);
 
 /* ---- introspection ------------------------------------------------------------------ */
 FCS_PHMM_API int fcs_pairhmm_get_stats(fcs_phmm_handle* h, fcs_phmm_stats* out);

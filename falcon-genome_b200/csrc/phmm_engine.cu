@@ -296,6 +296,8 @@ struct Planner {
       const uint64_t slots = (uint64_t)sm_count * 10;
       if (reads_x_haps <= slots) min_G = 32;
       else if (reads_x_haps / 2 <= slots) min_G = 16;
+      static const int force_min_g = (int)env_i64("FCS_PHMM_FORCE_MIN_G", -1);  // developer knob
+      if (force_min_g >= 0) min_G = force_min_g;
     }
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps;
@@ -516,27 +518,37 @@ struct Planner {
       qu.cap = f64_cap[q];
       qu.maxlh = f64_maxlh[q];
       P.queues.push_back(qu);
-      const ClassRef* k = f64_queue_class((int)q, P.f64_gcp >= 0);
-      F64Range* rr = nullptr;
-      for (auto& r : P.f64)
-        if (r.tk == k->tk) { rr = &r; break; }
-      if (!rr) {
-        P.f64.emplace_back();
-        rr = &P.f64.back();
-        rr->tk = k->tk;
-        rr->n_seg = 0;
-        rr->hs_cap = 0;
-        rr->hap_stage = 0;
-        rr->smem = 0;
+      // two candidate drains per queue: the throughput class of the queue and, for a short queue, the
+      // widest class covering the same reads (the FP64 phase of a mostly-FP32 batch is a handful of
+      // pairs whose serial chain is the whole cost)
+      const ClassRef* kt = f64_queue_class((int)q, P.f64_gcp >= 0);
+      const ClassRef* kw = select_class_wide(true, P.f64_gcp >= 0, kt->G * kt->R - 1, 32);
+      const uint32_t short_q = (uint32_t)sm_count * 2u;
+      const bool two = !force_double && kw && !(kw->G == kt->G && kw->R == kt->R);
+      for (int pass = 0; pass < (two ? 2 : 1); ++pass) {
+        const ClassRef* k = pass == 0 ? kt : kw;
+        F64Range* rr = nullptr;
+        for (auto& r : P.f64)
+          if (r.tk == k->tk) { rr = &r; break; }
+        if (!rr) {
+          P.f64.emplace_back();
+          rr = &P.f64.back();
+          rr->tk = k->tk;
+          rr->n_seg = 0;
+          rr->hs_cap = 0;
+          rr->hap_stage = 0;
+          rr->smem = 0;
+        }
+        if (rr->n_seg >= 32) return set_error(FCS_PHMM_EINVAL, "internal: more than 32 FP64 segments in one launch");
+        rr->seg_cls[rr->n_seg] = (uint16_t)k->cls;
+        rr->seg_qid[rr->n_seg] = (uint16_t)q;
+        rr->seg_G[rr->n_seg] = (uint16_t)k->G;
+        if (!two) { rr->seg_min[rr->n_seg] = 0; rr->seg_max[rr->n_seg] = 0xffffffffu; rr->seg_cap[rr->n_seg] = f64_cap[q]; }
+        else if (pass == 0) { rr->seg_min[rr->n_seg] = short_q + 1; rr->seg_max[rr->n_seg] = 0xffffffffu; rr->seg_cap[rr->n_seg] = f64_cap[q]; }
+        else { rr->seg_min[rr->n_seg] = 0; rr->seg_max[rr->n_seg] = short_q; rr->seg_cap[rr->n_seg] = std::min(f64_cap[q], short_q); }
+        rr->n_seg++;
+        rr->hap_stage = std::max(rr->hap_stage, round_up16(f64_maxlh[q]));
       }
-      if (rr->n_seg >= 16) return set_error(FCS_PHMM_EINVAL, "internal: more than 16 FP64 classes in one tier");
-      rr->seg_cls[rr->n_seg] = (uint16_t)k->cls;
-      rr->seg_qid[rr->n_seg] = (uint16_t)q;
-      rr->seg_cap[rr->n_seg] = f64_cap[q];
-      rr->seg_G[rr->n_seg] = (uint16_t)k->G;
-      rr->n_seg++;
-      rr->hs_cap = std::max(rr->hs_cap, f64_maxlh[q] + 2u * (uint32_t)(32 - 1));
-      rr->hap_stage = std::max(rr->hap_stage, round_up16(f64_maxlh[q]));
     }
     for (auto& r : P.f64) {
       // hs_cap / hap_stage are per lane group; use each class's own G for the stream padding bound
@@ -816,6 +828,8 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
       for (uint32_t k = 0; k < r.n_seg; ++k) {
         p.seg_cls[k] = r.seg_cls[k];
         p.seg_qid[k] = r.seg_qid[k];
+        p.seg_min[k] = r.seg_min[k];
+        p.seg_max[k] = r.seg_max[k];
         p.seg_cta0[k] = grid;
         const unsigned ng = 32u / r.seg_G[k];
         grid += std::min((r.seg_cap[k] + ng - 1) / ng, resident);

@@ -68,8 +68,8 @@ struct F64Queue {
 struct F64Range {
   const TierKernel* tk;
   uint32_t n_seg, hs_cap, hap_stage;
-  uint16_t seg_cls[16], seg_qid[16], seg_G[16];
-  uint32_t seg_cap[16];
+  uint16_t seg_cls[32], seg_qid[32], seg_G[32];
+  uint32_t seg_cap[32], seg_min[32], seg_max[32];
   size_t smem;
 };
 

@@ -28,6 +28,8 @@ namespace fcsphmm {
     while (k + 1 < p.n_seg && blockIdx.x >= p.seg_cta0[k + 1]) ++k;                                \
     const uint32_t qid = p.seg_qid[k], cta = blockIdx.x - p.seg_cta0[k];                           \
     const uint32_t nctas = p.seg_cta0[k + 1] - p.seg_cta0[k];                                      \
+    const uint32_t qlen = p.rerun_count[qid];                                                      \
+    if (qlen < p.seg_min[k] || qlen > p.seg_max[k]) return;                                        \
     switch (p.seg_cls[k]) { LIST_MACRO(PHMM_CASE_QUEUE) default: break; }                          \
   }
 

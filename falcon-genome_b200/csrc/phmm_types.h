@@ -72,9 +72,13 @@ struct KParams {
   // FP64 launches: the classes of one register tier share a launch; segment k drains queue seg_qid[k]
   // with tier-local class seg_cls[k] on CTAs [seg_cta0[k], seg_cta0[k+1])
   uint32_t n_seg;
-  uint16_t seg_cls[16];
-  uint16_t seg_qid[16];
-  uint32_t seg_cta0[17];
+  uint16_t seg_cls[32];
+  uint16_t seg_qid[32];
+  uint32_t seg_cta0[33];
+  // a segment runs only if seg_min[k] <= queue length <= seg_max[k]: a short queue is drained by the
+  // widest class (shortest serial chain per pair), a long one by the throughput class
+  uint32_t seg_min[32];
+  uint32_t seg_max[32];
   uint32_t hs_cap;         // u16 entries of haplotype stream in shared memory
   uint32_t hap_stage_bytes;  // bytes of raw haplotype staging in shared memory
   // generic (striped) path: host-built pair list for the FP32 pass, per-CTA boundary scratch rows

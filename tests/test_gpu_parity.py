@@ -29,8 +29,9 @@ def check_against_oracle(oracle, b, out, used, raw=None, simd=True):
     err = np.abs(out[fin] - o_ref[fin])
     assert err.max() <= TOL, f"max |dlog10L| = {err.max()}"
     # FP64 path: same operation order as the oracle -> agreement far below the tolerance
-    if used.any():
-        assert np.abs(out[used == 1] - o_ref[used == 1])[np.isfinite(o_ref[used == 1])].max() <= 1e-9
+    sel = (used == 1) & fin
+    if sel.any():
+        assert np.abs(out[sel] - o_ref[sel]).max() <= 1e-9
     if dbl is not None:
         assert np.abs(out[fin] - dbl[fin]).max() <= TOL  # vs the double-precision oracle for EVERY pair
     # per-read best haplotype (ties -> lowest h)
@@ -291,3 +292,31 @@ def test_concurrent_callers_on_one_handle(hmm):
     for t in th:
         t.join()
     assert not errs, errs[:3]
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103])
+def test_fuzz_random_shapes_and_bytes(hmm, oracle, seed):
+    """Randomised regions: any read length 1..420, haplotype length 1..700, quals over the whole byte
+    range (the kernels mask & 127), N and non-ACGT read bytes, uniform and per-base gap-continuation
+    quals mixed in one call (general and uniform-GCP kernels side by side)."""
+    rng = np.random.default_rng(seed)
+    regs = []
+    for _ in range(40):
+        nh = int(rng.integers(1, 6))
+        haps = [bytes(rng.choice(list(b"ACGTN"), int(rng.integers(1, 700)), p=[.24, .24, .24, .24, .04]).astype(np.uint8)) for _ in range(nh)]
+        reads = []
+        for _r in range(int(rng.integers(1, 12))):
+            L = int(rng.choice([rng.integers(1, 30), rng.integers(30, 200), rng.integers(200, 420)]))
+            src = haps[int(rng.integers(0, nh))]
+            b = bytearray((src * (L // len(src) + 2))[:L])
+            for k in rng.integers(0, L, max(1, L // 20)):
+                b[k] = int(rng.choice(list(b"ACGTNRYacgt")))
+            q = rng.integers(0, 256, L).astype(np.uint8) if rng.random() < 0.3 else rng.integers(2, 42, L).astype(np.uint8)
+            i = rng.integers(5, 60, L).astype(np.uint8)
+            d = rng.integers(5, 60, L).astype(np.uint8)
+            c = np.full(L, int(rng.integers(5, 40)), np.uint8) if rng.random() < 0.6 else rng.integers(5, 40, L).astype(np.uint8)
+            reads.append((bytes(b), bytes(q), bytes(i), bytes(d), bytes(c)))
+        regs.append(Region(reads, haps))
+    b = FlatBatch.from_regions(regs)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)

@@ -279,6 +279,7 @@ struct Planner {
     s.genlist.clear();
     s.gen_flags.clear();
     uint32_t gen64_cap = 0, gen_maxlh = 0;
+    bool any_n = false;  // some haplotype contains an N: the prior table needs its sixth symbol row
     // Latency policy for under-filled chunks: if even with one task per (4 reads x 1 haplotype) the chunk
     // cannot fill the one-warp CTA slots of the device, the call is latency bound: the time is the serial
     // chain of one task.  Then give every read the widest lane group (shortest chain per column) that still
@@ -338,6 +339,7 @@ struct Planner {
         if (h.len > FCS_PHMM_MAX_HAP_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype longer than FCS_PHMM_MAX_HAP_LEN");
         hlens[j] = (uint32_t)h.len;
         sum_h += (uint64_t)h.len;
+        if (!any_n && std::memchr(h.b, 'N', (size_t)h.len)) any_n = true;
         hb += round_up16((uint32_t)h.len);
       }
       const uint64_t cells = sum_r * sum_h;
@@ -446,6 +448,7 @@ struct Planner {
     // ---- layout
     size_t off = 0;
     P.latency_mode = min_G != 0;
+    P.n_sym = any_n ? 6u : 5u;
     P.off_reads = off; off = align_up(off + reads_bytes, 256);
     P.off_haps = off; off = align_up(off + haps_bytes, 256);
     P.off_rmeta = off; off = align_up(off + P.n_reads * sizeof(ReadMeta), 256);
@@ -493,7 +496,7 @@ struct Planner {
       r.max_task_cost = b.max_task_cost;
       r.smem = 0;
       for (int c = 0; c < b.tk->n_classes; ++c)
-        if (b.cls_mask >> c & 1ull) r.smem = std::max(r.smem, b.tk->classes[c].smem_bytes(b.hs, b.stage));
+        if (b.cls_mask >> c & 1ull) r.smem = std::max(r.smem, b.tk->classes[c].smem_bytes(b.hs, b.stage, P.n_sym));
       P.f32.push_back(r);
       P.n_tasks += r.n_tasks;
     }
@@ -560,7 +563,7 @@ struct Planner {
         hs = std::max(hs, mlh + 2u * (uint32_t)(r.seg_G[k] - 1));
       }
       r.hs_cap = hs;
-      for (uint32_t k = 0; k < r.n_seg; ++k) r.smem = std::max(r.smem, r.tk->classes[r.seg_cls[k]].smem_bytes(r.hs_cap, r.hap_stage));
+      for (uint32_t k = 0; k < r.n_seg; ++k) r.smem = std::max(r.smem, r.tk->classes[r.seg_cls[k]].smem_bytes(r.hs_cap, r.hap_stage, P.n_sym));
     }
     const size_t rerun_bytes = align_up(P.n_pairs * sizeof(RerunEntry), 256);
     if (force_double) { off += rerun_bytes; P.in_bytes = off; }
@@ -703,6 +706,7 @@ void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) 
   p.scratch = b + P.off_scratch;
   p.hs_cap = 0;
   p.hap_stage_bytes = 0;
+  p.n_sym = P.n_sym;
   p.c_xx_f = 0.f; p.c_gm_f = 0.f; p.c_xx_d = 0.0; p.c_gm_d = 0.0;
 }
 

@@ -88,6 +88,7 @@ struct ChunkPlan {
   std::vector<F64Range> f64;
   std::vector<F64Queue> queues;
   bool force_double = false;
+  uint32_t n_sym = 6;         // prior-table symbol rows (5 when no haplotype of the chunk contains an N)
   bool latency_mode = false;  // under-filled chunk: widest lane groups, one haplotype per task
   int f64_gcp = -1;  // >= 0: every read of the chunk shares this gap-continuation quality
   int launches() const;

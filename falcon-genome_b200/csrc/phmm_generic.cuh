@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32, 8) phmm_generic(const __grid_constant__ KP
     T result = T(0);
     for (int s = 0; s < P; ++s) {
       __syncwarp();
-      tile.build(rs, (uint32_t)Lr, lane, lut, mm, tab_lane, s * C::ROWS, npad);
+      tile.build(rs, (uint32_t)Lr, lane, lut, mm, tab_lane, true, s * C::ROWS, npad);
       __syncwarp();
       State st;
       tile.init(st, y_init);

@@ -111,6 +111,11 @@ __device__ __forceinline__ int base_code(uint32_t b) {
 
 // ----------------------------------------------------------------------------------------
 // shared-memory layout of one CTA
+//   [mbarrier 128 B][prior table: n_sym x 32 lanes x STRIDE][union][raw haplotype staging]
+//   union = { ph2pr LUT + read staging }  (needed until the tile is built)
+//         = { haplotype stream }          (written after the tile is built)
+// The N symbol row exists only if a haplotype of the launch contains an N (n_sym = 6).  Together
+// these keep the common 150-bp class at 12 one-warp CTAs per SM.
 template <typename T, int G, int R, bool LIST>
 struct Layout {
   static constexpr int NG = 32 / G;
@@ -122,14 +127,18 @@ struct Layout {
   static constexpr int VW = 16 / (int)sizeof(T);    // values per LDS.128
   static constexpr int RSTAGE = 5 * (int)round_up16(ROWS);   // read staging bytes per group
   static constexpr int OFF_BAR = 0;
-  static constexpr int OFF_LUT = 128;
-  static constexpr int OFF_TAB = OFF_LUT + 128 * (int)sizeof(T);
-  static constexpr int OFF_RSTAGE = OFF_TAB + kTabRows * SYM_PITCH;
-  static constexpr int OFF_DYN = OFF_RSTAGE + NG * RSTAGE;
+  static constexpr int OFF_TAB = 128;
+  static constexpr int LUT_BYTES = 128 * (int)sizeof(T);
+  static constexpr int PRE_BYTES = LUT_BYTES + NG * RSTAGE;
   static_assert(OFF_TAB % 128 == 0, "table must start on a 128-byte line");
+  PHMM_HD static constexpr uint32_t off_union(uint32_t n_sym) { return (uint32_t)OFF_TAB + n_sym * (uint32_t)SYM_PITCH; }
   // hs_cap / hap_stage_bytes are per group when LIST, per CTA otherwise
-  static constexpr size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage_bytes) {
-    return (size_t)OFF_DYN + (size_t)(LIST ? NG : 1) * (round_up16(hs_cap * 2u) + (size_t)round_up16(hap_stage_bytes));
+  PHMM_HD static constexpr uint32_t union_bytes(uint32_t hs_cap) {
+    const uint32_t hs = (uint32_t)(LIST ? NG : 1) * round_up16(hs_cap * 2u);
+    return hs > (uint32_t)PRE_BYTES ? hs : (uint32_t)PRE_BYTES;
+  }
+  static constexpr size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage_bytes, uint32_t n_sym) {
+    return (size_t)off_union(n_sym) + union_bytes(hs_cap) + (size_t)(LIST ? NG : 1) * round_up16(hap_stage_bytes);
   }
 };
 
@@ -167,7 +176,7 @@ struct Tile {
   // row0 / npad: tile row 0 of lane 0 is row `row0` of a striped read whose first `npad` rows are
   // boundary replicas (single pass: row0 = 0, npad = G*R - len).
   __device__ __forceinline__ void build(const uint8_t* rs, uint32_t len, int lig, const T* lut, const T* __restrict__ mm,
-                                        uint8_t* tab_lane, int row0 = 0, int npad_override = -1) {
+                                        uint8_t* tab_lane, bool with_n, int row0 = 0, int npad_override = -1) {
     const uint32_t Lp = round_up16(len);
     const int npad = (npad_override >= 0 ? npad_override : G * R - (int)len) - row0;
     padmask = 0;
@@ -211,12 +220,13 @@ struct Tile {
         if (k == 0) pYY[0] = yyk;
       }
 #pragma unroll
-      for (int h = 0; h < 5; ++h) {
-        const bool m = (h == kCodeN) || (rcode == kCodeN) || (rcode == h);
+      for (int h = 0; h < 4; ++h) {
+        const bool m = (rcode == kCodeN) || (rcode == h);
         const T v = (pos >= 0) ? (m ? pm : px) : T(0);
         *reinterpret_cast<T*>(tab_lane + h * (32 * STRIDE) + k * (int)sizeof(T)) = v;
       }
       *reinterpret_cast<T*>(tab_lane + kCodePad * (32 * STRIDE) + k * (int)sizeof(T)) = T(0);
+      if (with_n) *reinterpret_cast<T*>(tab_lane + kCodeN * (32 * STRIDE) + k * (int)sizeof(T)) = (pos >= 0) ? pm : T(0);
     }
   }
 
@@ -330,12 +340,12 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   const int lane = threadIdx.x;
   const int grp = lane / G, lig = lane % G;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  T* lut = reinterpret_cast<T*>(smem + L::OFF_LUT);
   uint8_t* tab_lane = smem + L::OFF_TAB + lane * L::STRIDE;
-  uint8_t* rstage = smem + L::OFF_RSTAGE + grp * L::RSTAGE;
-  const uint32_t hs_bytes = round_up16(p.hs_cap * 2u);
-  uint16_t* hs = reinterpret_cast<uint16_t*>(smem + L::OFF_DYN);
-  uint8_t* hstage = smem + L::OFF_DYN + hs_bytes;
+  uint8_t* un = smem + L::off_union(p.n_sym);
+  T* lut = reinterpret_cast<T*>(un);
+  uint8_t* rstage = un + L::LUT_BYTES + grp * L::RSTAGE;
+  uint16_t* hs = reinterpret_cast<uint16_t*>(un);  // aliases lut + rstage: written only after tile.build
+  uint8_t* hstage = un + L::union_bytes(p.hs_cap);
   const T* __restrict__ mm = reinterpret_cast<const T*>(p.mm);
 
   for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
@@ -361,7 +371,8 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
   mbar_wait(bar, 0u);
   // ---- per-row constants + prior table
-  tile.build(rstage, rlen, lig, lut, mm, tab_lane);
+  tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+  __syncwarp();  // every lane is done with the LUT and the read staging before the stream overwrites them
   // ---- haplotype stream: [G-1 PAD] hap0 [G-1 PAD] hap1 ... [G-1 PAD]
   uint32_t off = 0;
   for (uint32_t j = 0; j < task.n_haps; ++j) {
@@ -400,18 +411,18 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
   const int lane = threadIdx.x;
   const int grp = lane / G, lig = lane % G;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  T* lut = reinterpret_cast<T*>(smem + L::OFF_LUT);
   uint8_t* tab_lane = smem + L::OFF_TAB + lane * L::STRIDE;
-  uint8_t* rstage = smem + L::OFF_RSTAGE + grp * L::RSTAGE;
+  uint8_t* un = smem + L::off_union(p.n_sym);
+  T* lut = reinterpret_cast<T*>(un);
+  uint8_t* rstage = un + L::LUT_BYTES + grp * L::RSTAGE;
   const uint32_t hs_bytes = round_up16(p.hs_cap * 2u);
   const uint32_t hstage_bytes = round_up16(p.hap_stage_bytes);
-  uint16_t* hs = reinterpret_cast<uint16_t*>(smem + L::OFF_DYN) + grp * (hs_bytes / 2u);
-  uint8_t* hstage = smem + L::OFF_DYN + NG * hs_bytes + grp * hstage_bytes;
+  uint16_t* hs = reinterpret_cast<uint16_t*>(un) + grp * (hs_bytes / 2u);  // aliases lut + rstage
+  uint8_t* hstage = un + L::union_bytes(p.hs_cap) + grp * hstage_bytes;
   const T* __restrict__ mm = reinterpret_cast<const T*>(p.mm);
 
   const uint32_t count = p.rerun_count[qid];
   if (cta * NG >= count) return;
-  for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
   uint32_t parity = 0;
@@ -428,7 +439,9 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
     const HapMeta hm = p.hmeta[e.hap];
     const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
     const uint32_t Lh = active ? hm.len : 0u;
-    fence_proxy_async();  // staging was read through the generic proxy last round
+    // the LUT shares its shared memory with the haplotype stream of the previous round: reload it
+    for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
+    fence_proxy_async();  // staging / stream were touched through the generic proxy last round
     const uint32_t my_bytes = (active && lig == 0) ? 5u * round_up16(rlen) + round_up16(Lh) : 0u;
     const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
     if (lane == 0) mbar_expect_tx(bar, tot);
@@ -439,7 +452,8 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
     }
     mbar_wait(bar, parity);
     parity ^= 1u;
-    tile.build(rstage, rlen, lig, lut, mm, tab_lane);
+    tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+    __syncwarp();  // done with the LUT and the read staging before the stream overwrites them
     const uint32_t Lmax = __reduce_max_sync(0xffffffffu, Lh);
     const uint32_t total = Lmax + 2u * (G - 1);
     for (uint32_t x = lig; x < total; x += G) {

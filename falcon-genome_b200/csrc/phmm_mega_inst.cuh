@@ -6,8 +6,8 @@
 namespace fcsphmm {
 
 template <typename T, int G, int R, bool LIST>
-size_t class_smem_bytes(uint32_t hs_cap, uint32_t hap_stage_bytes) {
-  return Layout<T, G, R, LIST>::smem_bytes(hs_cap, hap_stage_bytes);
+size_t class_smem_bytes(uint32_t hs_cap, uint32_t hap_stage_bytes, uint32_t n_sym) {
+  return Layout<T, G, R, LIST>::smem_bytes(hs_cap, hap_stage_bytes, n_sym);
 }
 
 #define PHMM_CLASSDESC_F32(I, G, R) {G, R, &class_smem_bytes<float, G, R, false>},

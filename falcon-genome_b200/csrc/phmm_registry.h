@@ -11,7 +11,7 @@ namespace fcsphmm {
 
 struct ClassDesc {
   int G, R;
-  size_t (*smem_bytes)(uint32_t hs_cap, uint32_t hap_stage_bytes);
+  size_t (*smem_bytes)(uint32_t hs_cap, uint32_t hap_stage_bytes, uint32_t n_sym);
 };
 
 struct TierKernel {
@@ -29,7 +29,7 @@ struct ClassRef {
   const TierKernel* tk;
   int cls;  // index inside tk->classes == Task::cls / KParams::seg_cls
   int G, R;
-  size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage) const { return tk->classes[cls].smem_bytes(hs_cap, hap_stage); }
+  size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage, uint32_t n_sym) const { return tk->classes[cls].smem_bytes(hs_cap, hap_stage, n_sym); }
 };
 
 // All compiled kernels (12), terminated by launch == nullptr.

@@ -21,9 +21,9 @@
 
 namespace fcsphmm {
 
-constexpr int kTabRows = 6;  // haplotype symbol classes: A C G T N PAD
-constexpr int kCodeN = 4;
-constexpr int kCodePad = 5;
+constexpr int kTabRows = 6;  // haplotype symbol classes: A C G T PAD N  (N last: its table row is
+constexpr int kCodePad = 4;  //   allocated only when some haplotype of the launch contains an N)
+constexpr int kCodeN = 5;
 constexpr int kMaxF64Classes = 40;
 constexpr int kQueueGenericF64 = kMaxF64Classes - 1;  // FP64 rerun queue of the striped generic path
 
@@ -81,6 +81,7 @@ struct KParams {
   uint32_t seg_max[32];
   uint32_t hs_cap;         // u16 entries of haplotype stream in shared memory
   uint32_t hap_stage_bytes;  // bytes of raw haplotype staging in shared memory
+  uint32_t n_sym;            // prior-table symbol rows in shared memory: 5 (no N in any haplotype) or 6
   // generic (striped) path: host-built pair list for the FP32 pass, per-CTA boundary scratch rows
   const RerunEntry* gen_list;
   uint32_t gen_count;

@@ -389,7 +389,7 @@ struct Planner {
         int tg = gcps[ord[i]];  // uniform-GCP form only if every read of the task shares the value
         for (int32_t x = 1; x < cnt; ++x)
           if (gcps[ord[i + x]] != tg) tg = -1;
-        const ClassRef* kc = tg >= 0 ? find_class(false, true, k0->G, k0->R) : k0;
+        const ClassRef* kc = (tg >= 0 && k0->twin) ? k0->twin : k0;
         TaskBucket* bk = nullptr;
         for (auto& b : s.buckets)
           if (b.tk == kc->tk && b.gcp == tg) { bk = &b; break; }
@@ -471,14 +471,16 @@ struct Planner {
           for (uint32_t j = 0; j < x.n_haps; ++j) cols += hap_len_chunk[x.hap0 + j] + (uint32_t)cd.G - 1u;
           key[t] = {(uint32_t)cd.R * cols, t};
         }
-        std::stable_sort(key.begin(), key.end(), [&](const auto& a, const auto& c) {
+        auto before = [&](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& c) {
           const Task &ta = b.tasks[a.second], &tc = b.tasks[c.second];
           if (ta.cls != tc.cls) {
             const ClassDesc &ca = b.tk->classes[ta.cls], &cc = b.tk->classes[tc.cls];
             if (ca.R != cc.R) return ca.R > cc.R;
             return ca.G > cc.G;
           }
-          return a.first > c.first; });
+          return a.first > c.first;
+        };
+        if (!std::is_sorted(key.begin(), key.end(), before)) std::stable_sort(key.begin(), key.end(), before);
         std::vector<Task> sorted(n);
         for (uint32_t t = 0; t < n; ++t) sorted[t] = b.tasks[key[t].second];
         b.tasks.swap(sorted);
@@ -922,11 +924,19 @@ void WorkerPool::drain() {
 void WorkerPool::loop() {
   uint64_t seen = 0;
   for (;;) {
+    // Calls arrive back to back (one per active region or per batch): spin briefly for the next one
+    // before sleeping, a condition-variable wake-up costs tens of microseconds of a ~2 ms call.
+    const double t0 = now_ms();
+    while (gen_.load(std::memory_order_acquire) == seen && now_ms() - t0 < 0.2) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
     {
       std::unique_lock<std::mutex> lk(mu_);
-      cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+      cv_.wait(lk, [&] { return stop_ || gen_.load() != seen; });
       if (stop_) return;
-      seen = gen_;
+      seen = gen_.load();
     }
     drain();
   }
@@ -939,7 +949,7 @@ void WorkerPool::run(int n_jobs, const std::function<void(int)>& fn) {
     n_jobs_ = n_jobs;
     pending_ = n_jobs;
     next_.store(0);
-    ++gen_;
+    gen_.fetch_add(1, std::memory_order_release);
   }
   cv_.notify_all();
   drain();  // the caller works too

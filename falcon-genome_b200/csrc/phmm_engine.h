@@ -152,7 +152,7 @@ class WorkerPool {
   const std::function<void(int)>* fn_ = nullptr;
   int n_jobs_ = 0, pending_ = 0;
   std::atomic<int> next_{0};
-  uint64_t gen_ = 0;
+  std::atomic<uint64_t> gen_{0};
   bool stop_ = false;
 };
 

@@ -36,7 +36,7 @@ void build() {
   for (int i = 0; i < kNumKernels; ++i) {
     const TierKernel* tk = g_kernels[i];
     auto& v = g_classes[(tk->f64 ? 2 : 0) + (tk->ug ? 1 : 0)];
-    for (int c = 0; c < tk->n_classes; ++c) v.push_back(ClassRef{tk, c, tk->classes[c].G, tk->classes[c].R});
+    for (int c = 0; c < tk->n_classes; ++c) v.push_back(ClassRef{tk, c, tk->classes[c].G, tk->classes[c].R, nullptr});
   }
   for (int f = 0; f < 4; ++f) {
     g_sel[f].assign(kMaxSelLen + 1, nullptr);
@@ -52,6 +52,10 @@ void build() {
     }
   }
   for (const ClassRef& k : g_classes[2]) g_f64_queues.emplace_back(k.G, k.R);
+  for (int f = 0; f < 4; ++f)
+    for (ClassRef& k : g_classes[f])
+      for (const ClassRef& o : g_classes[f ^ 1])
+        if (o.G == k.G && o.R == k.R) { k.twin = &o; break; }
 }
 }  // namespace
 

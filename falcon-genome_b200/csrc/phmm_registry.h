@@ -29,6 +29,7 @@ struct ClassRef {
   const TierKernel* tk;
   int cls;  // index inside tk->classes == Task::cls / KParams::seg_cls
   int G, R;
+  const ClassRef* twin = nullptr;  // the same (G, R) in the other GCP form (general <-> uniform)
   size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage, uint32_t n_sym) const { return tk->classes[cls].smem_bytes(hs_cap, hap_stage, n_sym); }
 };
 

@@ -47,6 +47,12 @@ class PrepParams(C.Structure):
                 ("pcr_model", C.c_int32)]
 
 
+class PlanInfo(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("n_tasks", C.c_int64), ("n_generic_pairs", C.c_int64), ("in_bytes", C.c_int64),
+                ("max_smem_bytes", C.c_int64), ("n_launches_f32", C.c_int32), ("n_launches_f64", C.c_int32), ("n_sym", C.c_int32),
+                ("latency_mode", C.c_int32), ("geometric_efficiency", C.c_double), ("plan_ms", C.c_double), ("pack_ms", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("cells", C.c_uint64), ("fp64_pairs", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("chunks", C.c_uint64), ("kernel_ms", C.c_double),
@@ -88,6 +94,7 @@ SIGNATURES = {
     "fcs_pairhmm_capture_free": (None, [C.c_void_p]),
     "fcs_pairhmm_prepare_read": (C.c_int, [u8p, u8p, C.c_int32, C.c_int32, u8p, u8p, C.POINTER(PrepParams), u8p, u8p, u8p, u8p]),
     "fcs_pairhmm_finalize_region": (C.c_int, [f64p, C.c_int32, C.c_int32, i32p, C.c_double, C.c_double, u8p]),
+    "fcs_pairhmm_plan_check": (C.c_int, [C.POINTER(FlatStruct), C.c_int32, C.POINTER(PlanInfo)]),
     "fcs_pairhmm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "fcs_pairhmm_reset_stats": (C.c_int, [C.c_void_p]),
     "fcs_pairhmm_lut_ph2pr_f32": (C.c_float, [C.c_int]),

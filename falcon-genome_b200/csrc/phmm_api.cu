@@ -271,6 +271,15 @@ int fcs_pairhmm_finalize_region(double* log10_likelihoods, int32_t n_reads, int3
   API_CATCH
 }
 
+int fcs_pairhmm_plan_check(const fcs_phmm_flat_batch* b, int32_t sm_count, fcs_phmm_plan_info* out) {
+  if (!out) return set_error(FCS_PHMM_EINVAL, "null out");
+  API_TRY
+  int rc = check_flat(b);
+  if (rc != FCS_PHMM_OK) return rc;
+  return plan_check(b, sm_count, out);
+  API_CATCH
+}
+
 float fcs_pairhmm_lut_ph2pr_f32(int q) { return luts().ph2pr_f[q & 127]; }
 double fcs_pairhmm_lut_ph2pr_f64(int q) { return luts().ph2pr_d[q & 127]; }
 float fcs_pairhmm_lut_mm_f32(int i, int d) { return luts().mm_f[mm_index(i & 127, d & 127)]; }

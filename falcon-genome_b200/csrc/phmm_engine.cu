@@ -71,8 +71,15 @@ static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid
 // The value all gap-continuation quals of a read share (masked & 127 like the kernels), or -1.
 static int uniform_gcp(const uint8_t* c, int32_t len) {
   const uint8_t v = c[0] & 127u;
-  uint8_t diff = 0;
-  for (int32_t i = 1; i < len; ++i) diff |= (uint8_t)((c[i] & 127u) ^ v);
+  const uint64_t vv = 0x0101010101010101ull * v, m7 = 0x7f7f7f7f7f7f7f7full;
+  uint64_t diff = 0;
+  int32_t i = 0;
+  for (; i + 8 <= len; i += 8) {  // eight quals per step (this scan runs over every read of every call)
+    uint64_t w;
+    std::memcpy(&w, c + i, 8);
+    diff |= (w & m7) ^ vv;
+  }
+  for (; i < len; ++i) diff |= (uint64_t)((c[i] & 127u) ^ v);
   return diff ? -1 : (int)v;
 }
 
@@ -463,29 +470,46 @@ struct Planner {
       // classes freely (pure longest-first) thrashes the instruction cache (C3: 2.5 -> 0.9 TCUPS).
       {
         const uint32_t n = (uint32_t)b.tasks.size();
-        std::vector<std::pair<uint32_t, uint32_t>> key(n);
+        // one integer key per task: class rank (rows per lane desc, lanes desc) in the high half, inverted cost below
+        std::vector<uint32_t> rank((size_t)b.tk->n_classes);
+        {
+          std::vector<int> byrank((size_t)b.tk->n_classes);
+          std::iota(byrank.begin(), byrank.end(), 0);
+          std::sort(byrank.begin(), byrank.end(), [&](int x, int y) {
+            const ClassDesc &cx = b.tk->classes[x], &cy = b.tk->classes[y];
+            return cx.R != cy.R ? cx.R > cy.R : cx.G > cy.G; });
+          for (size_t r2 = 0; r2 < byrank.size(); ++r2) rank[(size_t)byrank[r2]] = (uint32_t)r2;
+        }
+        std::vector<uint32_t> cost(n);
+        b.max_task_cost = 0;
         for (uint32_t t = 0; t < n; ++t) {
           const Task& x = b.tasks[t];
           const ClassDesc& cd = b.tk->classes[x.cls];
           uint32_t cols = 0;
           for (uint32_t j = 0; j < x.n_haps; ++j) cols += hap_len_chunk[x.hap0 + j] + (uint32_t)cd.G - 1u;
-          key[t] = {(uint32_t)cd.R * cols, t};
+          cost[t] = (uint32_t)cd.R * cols;
+          b.max_task_cost = std::max(b.max_task_cost, cost[t]);
         }
-        auto before = [&](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& c) {
-          const Task &ta = b.tasks[a.second], &tc = b.tasks[c.second];
-          if (ta.cls != tc.cls) {
-            const ClassDesc &ca = b.tk->classes[ta.cls], &cc = b.tk->classes[tc.cls];
-            if (ca.R != cc.R) return ca.R > cc.R;
-            return ca.G > cc.G;
-          }
-          return a.first > c.first;
-        };
-        if (!std::is_sorted(key.begin(), key.end(), before)) std::stable_sort(key.begin(), key.end(), before);
-        std::vector<Task> sorted(n);
-        for (uint32_t t = 0; t < n; ++t) sorted[t] = b.tasks[key[t].second];
-        b.tasks.swap(sorted);
-        b.max_task_cost = 0;
-        for (uint32_t t = 0; t < n; ++t) b.max_task_cost = std::max(b.max_task_cost, key[t].first);
+        // stable counting sort on (class rank, cost quantised to 256 levels, descending): O(n); the order
+        // inside a level is planning order -- longest-first is a heuristic, exact ties do not matter
+        const uint32_t nb = (uint32_t)b.tk->n_classes * 256u;
+        std::vector<uint32_t> start(nb + 1, 0), slot(n);
+        const uint64_t mc = std::max<uint32_t>(b.max_task_cost, 1u);
+        bool ordered = true;
+        uint32_t prev = 0;
+        for (uint32_t t = 0; t < n; ++t) {
+          const uint32_t q = 255u - (uint32_t)((uint64_t)cost[t] * 255u / mc);
+          slot[t] = rank[b.tasks[t].cls] * 256u + q;
+          ordered = ordered && slot[t] >= prev;
+          prev = slot[t];
+          ++start[slot[t] + 1];
+        }
+        if (!ordered) {
+          for (uint32_t i = 0; i < nb; ++i) start[i + 1] += start[i];
+          std::vector<Task> sorted(n);
+          for (uint32_t t = 0; t < n; ++t) sorted[start[slot[t]]++] = b.tasks[t];
+          b.tasks.swap(sorted);
+        }
       }
       F32Range r;
       r.tk = b.tk;
@@ -603,7 +627,9 @@ static const uint8_t* hap_valid_lut() {
 }
 
 // Pass 2: copy reads / quals / haplotypes into the pinned staging buffer in device layout.
-int Engine::pack_chunk(Slot& s, const Input& in) {
+int Engine::pack_chunk(Slot& s, const Input& in) { return pack_chunk_static(s, in); }
+
+int Engine::pack_chunk_static(Slot& s, const Input& in) {
   ChunkPlan& P = s.plan;
   uint8_t* base = s.h_in;
   ReadMeta* rmeta = reinterpret_cast<ReadMeta*>(base + P.off_rmeta);
@@ -1265,6 +1291,88 @@ void Engine::batch_destroy(Batch* b) {
   cudaSetDevice(devs_[b->device_index]->ordinal);
   free_slot(b->slot);
   delete b;
+}
+
+// Host-only: plan + pack a batch as one chunk exactly as compute() would (no device needed), check that
+// the tasks and the generic pair list cover every (read, hap) pair exactly once, and report what the
+// batcher decided.  Used by the CPU tests and to profile the host path.
+int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* out) {
+  std::call_once(g_cls_once, build_len_tables);
+  std::memset(out, 0, sizeof(*out));
+  static double dummy_out;
+  std::unique_ptr<Input> in = make_flat_input(*fb, &dummy_out, nullptr, nullptr);
+  Slot s;
+  std::vector<int64_t> regs((size_t)fb->n_regions);
+  std::iota(regs.begin(), regs.end(), (int64_t)0);
+  size_t next = 0;
+  const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
+  const double t0 = now_ms();
+  Planner pl{*in, s, false, false, INT64_MAX, hs_cols, sm_count > 0 ? sm_count : 148};
+  int rc = pl.run(regs, 0, next);
+  if (rc != FCS_PHMM_OK) return rc;
+  if (next != regs.size()) return set_error(FCS_PHMM_EUNSUPPORTED, "batch too large for one chunk");
+  const double t1 = now_ms();
+  ChunkPlan& P = s.plan;
+  std::vector<uint8_t> buf(P.in_bytes + 256);  // touched here, so the pack time below excludes page faults
+  s.h_in = buf.data();
+  const double t1b = now_ms();
+  Engine* e = nullptr;
+  (void)e;
+  // pack_chunk is a member only for historical reasons; it touches nothing but the slot
+  rc = Engine::pack_chunk_static(s, *in);
+  s.h_in = nullptr;
+  if (rc != FCS_PHMM_OK) return rc;
+  const double t2 = now_ms();
+  out->plan_ms = t1 - t0;
+  out->pack_ms = t2 - t1b;
+  out->n_pairs = (int64_t)P.n_pairs;
+  out->n_tasks = (int64_t)P.n_tasks;
+  out->n_generic_pairs = (int64_t)P.n_gen;
+  out->n_launches_f32 = 0;
+  for (const auto& r : P.f32) out->n_launches_f32 += r.n_tasks ? 1 : 0;
+  out->n_launches_f32 += P.n_gen ? 1 : 0;
+  out->n_launches_f64 = (int32_t)P.f64.size() + (P.gen64_cap ? 1 : 0);
+  out->n_sym = (int32_t)P.n_sym;
+  out->latency_mode = P.latency_mode ? 1 : 0;
+  out->in_bytes = (int64_t)P.in_bytes;
+  // ---- coverage: every (read, hap) pair exactly once
+  const ReadMeta* rm = reinterpret_cast<const ReadMeta*>(buf.data() + P.off_rmeta);
+  const HapMeta* hm = reinterpret_cast<const HapMeta*>(buf.data() + P.off_hmeta);
+  std::vector<uint8_t> seen((size_t)P.n_pairs, 0);
+  double swept = 0, useful = 0;
+  size_t max_smem = 0;
+  for (const F32Range& r : P.f32) {
+    max_smem = std::max(max_smem, r.smem);
+    const TaskBucket& bk = s.buckets[r.bucket];
+    for (const Task& t : bk.tasks) {
+      const ClassDesc& cd = r.tk->classes[t.cls];
+      if ((int)t.n_reads > 32 / cd.G || t.n_reads == 0 || t.n_haps == 0) return set_error(FCS_PHMM_EINVAL, "plan_check: task shape");
+      double cols = 0, hl = 0, rl = 0;
+      for (uint32_t j = 0; j < t.n_haps; ++j) { cols += hm[t.hap0 + j].len + cd.G - 1; hl += hm[t.hap0 + j].len; }
+      for (uint32_t i = 0; i < t.n_reads; ++i) {
+        const ReadMeta& m = rm[t.read0 + i];
+        const uint32_t len = m.len_cls & 0xffffffu;
+        if ((int)len + 1 > cd.G * cd.R) return set_error(FCS_PHMM_EINVAL, "plan_check: class does not cover the read");
+        rl += len;
+        for (uint32_t j = 0; j < t.n_haps; ++j) {
+          const uint32_t oi = m.out_off + (t.hap0 + j - m.hap0);
+          if (oi >= P.n_pairs || seen[oi]++) return set_error(FCS_PHMM_EINVAL, "plan_check: pair covered twice or out of range");
+        }
+      }
+      swept += 32.0 * cd.R * cols;
+      useful += rl * hl;
+    }
+  }
+  for (const RerunEntry& e2 : s.genlist) {
+    const ReadMeta& m = rm[e2.read];
+    const uint32_t oi = m.out_off + (e2.hap - m.hap0);
+    if (oi >= P.n_pairs || seen[oi]++) return set_error(FCS_PHMM_EINVAL, "plan_check: generic pair covered twice or out of range");
+  }
+  for (uint8_t v : seen)
+    if (v != 1) return set_error(FCS_PHMM_EINVAL, "plan_check: a pair is not covered");
+  out->geometric_efficiency = swept > 0 ? useful / swept : 1.0;
+  out->max_smem_bytes = (int64_t)max_smem;
+  return FCS_PHMM_OK;
 }
 
 int Engine::get_stats(fcs_phmm_stats* s) {

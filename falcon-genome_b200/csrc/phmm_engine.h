@@ -174,6 +174,7 @@ class Engine {
   int get_stats(fcs_phmm_stats* s);
   void reset_stats();
   int device_count() const { return (int)devs_.size(); }
+  static int pack_chunk_static(Slot& s, const Input& in);
   int set_capture(const char* path);  // nullptr / empty = stop capturing
 
  private:
@@ -216,6 +217,8 @@ struct Batch {
 int prepare_read(const uint8_t* bases, const uint8_t* raw_q, int32_t len, int32_t mapq, const uint8_t* bam_ins, const uint8_t* bam_del,
                  const fcs_phmm_prep_params* pp, uint8_t* out_q, uint8_t* out_i, uint8_t* out_d, uint8_t* out_c);
 int finalize_region(double* l, int32_t n_reads, int32_t n_haps, const int32_t* read_len, double log10_mismap, double err_rate, uint8_t* poorly);
+
+int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* out);
 
 std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw);
 

@@ -3,6 +3,7 @@
 #include "phmm_registry.h"
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -74,6 +75,16 @@ const ClassRef* select_class(bool f64, bool ug, int read_len) {
 const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, int avg_hap_len) {
   std::call_once(g_once, build);
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
+  // memo: the choice depends on the haplotype length only weakly -> four length bins; benign races
+  // (every thread computes the same pointer)
+  static std::atomic<const ClassRef*> memo[4][kMaxSelLen + 1][8][4];
+  const int nb = n_reads < 1 ? 1 : (n_reads > 7 ? 7 : n_reads);
+  const int hb = avg_hap_len < 150 ? 0 : (avg_hap_len < 300 ? 1 : (avg_hap_len < 600 ? 2 : 3));
+  static const int hb_len[4] = {100, 220, 420, 900};
+  std::atomic<const ClassRef*>& slot = memo[(f64 ? 2 : 0) + (ug ? 1 : 0)][read_len][nb][hb];
+  if (const ClassRef* hit = slot.load(std::memory_order_relaxed)) return hit;
+  n_reads = nb;
+  avg_hap_len = hb_len[hb];
   const ClassRef* best = nullptr;
   double bc = 0;
   const double lh = avg_hap_len > 0 ? avg_hap_len : 300;
@@ -83,6 +94,7 @@ const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, i
     const double c = step_cost(f64, k.R) * (lh + k.G - 1) / served;
     if (!best || c < bc * 0.999) { best = &k; bc = c; }
   }
+  slot.store(best, std::memory_order_relaxed);
   return best;
 }
 

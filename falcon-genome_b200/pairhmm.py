@@ -245,6 +245,17 @@ class PairHMM:
         self._check(self._lib.fcs_pairhmm_reset_stats(self._h))
 
 
+def plan_check(b: FlatBatch, sm_count: int = 148) -> dict:
+    """Run the batcher on the host (no GPU): verifies pair coverage, returns its decisions and timings."""
+    lib = _lib.load()
+    fs = _flat_struct(b)
+    info = _lib.PlanInfo()
+    rc = lib.fcs_pairhmm_plan_check(C.byref(fs), sm_count, C.byref(info))
+    if rc != _lib.OK:
+        raise PairHMMError(rc, (lib.fcs_pairhmm_last_error(None) or b"").decode())
+    return {f: getattr(info, f) for f, _ in _lib.PlanInfo._fields_}
+
+
 def kernel_class(read_len: int, fp64: bool = False) -> Tuple[int, int]:
     lib = _lib.load()
     g = C.c_int32()

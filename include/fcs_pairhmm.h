@@ -229,6 +229,15 @@ FCS_PHMM_API void fcs_pairhmm_remote_close(fcs_phmm_remote* r);
 /* ---- introspection ------------------------------------------------------------------ */
 FCS_PHMM_API int fcs_pairhmm_get_stats(fcs_phmm_handle* h, fcs_phmm_stats* out);
 FCS_PHMM_API int fcs_pairhmm_reset_stats(fcs_phmm_handle* h);
+/* Host-only: run the batcher on a batch (one chunk, no device needed), verify that its tasks cover every
+ * (read, hap) pair exactly once with classes that fit the reads, and report its decisions. */
+typedef struct {
+  int64_t n_pairs, n_tasks, n_generic_pairs, in_bytes, max_smem_bytes;
+  int32_t n_launches_f32, n_launches_f64, n_sym, latency_mode;
+  double geometric_efficiency; /* useful cells / cells swept by the tiles of the FP32 tasks */
+  double plan_ms, pack_ms;
+} fcs_phmm_plan_info;
+FCS_PHMM_API int fcs_pairhmm_plan_check(const fcs_phmm_flat_batch* b, int32_t sm_count, fcs_phmm_plan_info* out);
 /* The transition / prior lookup tables the kernels use, for bit-level checks against the oracle
  * (host-side, needs no device): ph2pr[q], matchToMatch(i,d) in float and double. */
 FCS_PHMM_API float fcs_pairhmm_lut_ph2pr_f32(int q);

@@ -98,3 +98,32 @@ def test_world_size_2_shard_compute_gather(tmp_path):
                         "--master-port", "29731", str(w), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GLOO-OK" in r.stdout
+
+
+def test_batcher_covers_every_pair_exactly_once():
+    """fcs_pairhmm_plan_check runs the real planner + packer on the host and verifies that the FP32 tasks and
+    the striped-path pair list cover every (read, hap) pair exactly once with classes that fit the reads."""
+    from falcon_genome_b200 import plan_check
+
+    rng = np.random.default_rng(9)
+    regs = []
+    for _ in range(60):
+        nh = int(rng.integers(1, 9))
+        haps = [bytes(rng.choice(list(b"ACGTN"), int(rng.choice([rng.integers(1, 50), rng.integers(50, 700), rng.integers(1900, 2300)]))).astype(np.uint8))
+                for _ in range(nh)]
+        reads = []
+        for _r in range(int(rng.integers(1, 40))):
+            L = int(rng.choice([rng.integers(1, 30), rng.integers(30, 260), rng.integers(260, 900)]))
+            reads.append((bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8)), bytes([30] * L), bytes([45] * L), bytes([45] * L),
+                          bytes([10] * L) if rng.random() < 0.7 else bytes(rng.integers(5, 30, L).astype(np.uint8))))
+        regs.append(Region(reads, haps))
+    b = FlatBatch.from_regions(regs)
+    info = plan_check(b)
+    assert info["n_pairs"] == b.n_pairs and info["n_generic_pairs"] > 0 and info["n_tasks"] > 0
+    assert info["max_smem_bytes"] <= 227 * 1024 and info["n_sym"] == 6
+    for mk, lo in ((synth.config2_uniform, 0.95), (synth.config1_golden, 0.90)):
+        bb = mk(n_regions=40)
+        i2 = plan_check(bb)
+        assert i2["n_pairs"] == bb.n_pairs and i2["n_generic_pairs"] == 0 and i2["geometric_efficiency"] >= lo and i2["n_sym"] == 5
+    tiny = plan_check(synth.tiny_mixed(seed=2, n_regions=2))
+    assert tiny["latency_mode"] == 1  # an under-filled call switches to the widest lane groups

@@ -1316,10 +1316,7 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
   std::vector<uint8_t> buf(P.in_bytes + 256);  // touched here, so the pack time below excludes page faults
   s.h_in = buf.data();
   const double t1b = now_ms();
-  Engine* e = nullptr;
-  (void)e;
-  // pack_chunk is a member only for historical reasons; it touches nothing but the slot
-  rc = Engine::pack_chunk_static(s, *in);
+  rc = Engine::pack_chunk_static(s, *in);  // touches nothing but the slot
   s.h_in = nullptr;
   if (rc != FCS_PHMM_OK) return rc;
   const double t2 = now_ms();

@@ -991,7 +991,78 @@ void WorkerPool::run(int n_jobs, const std::function<void(int)>& fn) {
 // --native-pair-hmm-threads, src/workers/HTCWorker.cpp:85) each plan + pack + launch whole chunks on
 // their own pair of slots, so packing chunk k+1 overlaps the device work of chunk k and chunks of
 // different threads overlap on the device.
+namespace {
+// Several callers' inputs seen as one: region g of the batch is region (g - first[c]) of call c.
+class CombinedInput : public Input {
+ public:
+  explicit CombinedInput(const std::vector<const Input*>& parts) : parts_(parts) {
+    first_.push_back(0);
+    for (const Input* p : parts_) first_.push_back(first_.back() + p->n_regions());
+  }
+  int64_t n_regions() const override { return first_.back(); }
+  void shape(int64_t g, int32_t& nr, int32_t& nh) const override { const auto w = where(g); parts_[w.first]->shape(w.second, nr, nh); }
+  InRead read(int64_t g, int32_t i) const override { const auto w = where(g); return parts_[w.first]->read(w.second, i); }
+  InHap hap(int64_t g, int32_t j) const override { const auto w = where(g); return parts_[w.first]->hap(w.second, j); }
+  double* out(int64_t g) const override { const auto w = where(g); return parts_[w.first]->out(w.second); }
+  uint8_t* used(int64_t g) const override { const auto w = where(g); return parts_[w.first]->used(w.second); }
+  float* raw(int64_t g) const override { const auto w = where(g); return parts_[w.first]->raw(w.second); }
+
+ private:
+  std::pair<size_t, int64_t> where(int64_t g) const {
+    const size_t c = (size_t)(std::upper_bound(first_.begin(), first_.end(), g) - first_.begin()) - 1;
+    return {c, g - first_[c]};
+  }
+  std::vector<const Input*> parts_;
+  std::vector<int64_t> first_;
+};
+}  // namespace
+
+// GATK calls the native PairHMM once per active region from several threads (--native-pair-hmm-threads,
+// /root/reference/src/workers/HTCWorker.cpp:85); one region is far too little work for a B200.  Callers that
+// arrive while a batch is on the device are queued; whoever finds no leader becomes the leader and runs
+// everything queued so far as ONE batch (flat combining).  Results are independent of the batching, so the
+// merge is invisible to the callers; if a merged batch fails, its calls are re-run one by one so that each
+// caller gets its own error.
 int Engine::compute(const Input& in) {
+  PendingCall me;
+  me.in = &in;
+  std::unique_lock<std::mutex> lk(comb_mu_);
+  comb_queue_.push_back(&me);
+  while (!me.done) {
+    if (comb_leader_) {
+      comb_cv_.wait(lk);
+      continue;
+    }
+    comb_leader_ = true;
+    std::vector<PendingCall*> batch;
+    batch.swap(comb_queue_);
+    lk.unlock();
+    if (batch.size() == 1) {
+      batch[0]->rc = compute_one(*batch[0]->in);
+      if (batch[0]->rc != FCS_PHMM_OK) batch[0]->err = last_error();
+    } else {
+      std::vector<const Input*> parts;
+      for (PendingCall* c : batch) parts.push_back(c->in);
+      CombinedInput all(parts);
+      int rc = compute_one(all);
+      if (rc != FCS_PHMM_OK) {
+        for (PendingCall* c : batch) {
+          c->rc = compute_one(*c->in);
+          if (c->rc != FCS_PHMM_OK) c->err = last_error();
+        }
+      }
+    }
+    lk.lock();
+    for (PendingCall* c : batch) c->done = true;
+    comb_leader_ = false;
+    comb_cv_.notify_all();
+  }
+  lk.unlock();
+  if (me.rc != FCS_PHMM_OK) return set_error(me.rc, me.err);
+  return FCS_PHMM_OK;
+}
+
+int Engine::compute_one(const Input& in) {
   const int64_t n = in.n_regions();
   if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
   if (n == 0) return FCS_PHMM_OK;

@@ -163,7 +163,8 @@ class Engine {
  public:
   static int create(const fcs_phmm_config* cfg, Engine** out);
   ~Engine();
-  int compute(const Input& in);
+  int compute(const Input& in);       // coalesces concurrent callers into one device batch
+  int compute_one(const Input& in);   // one batch, caller holds the device (compute_mu_)
   int submit(std::unique_ptr<Input> in, std::shared_ptr<void> keepalive, fcs_phmm_ticket* t);
   int wait(fcs_phmm_ticket t);
   int batch_create(const fcs_phmm_flat_batch* b, int device_index, Batch** out);
@@ -202,7 +203,19 @@ class Engine {
   fcs_phmm_ticket next_ticket_ = 1;
   std::unique_ptr<CaptureWriter> capture_;
   std::unique_ptr<WorkerPool> pool_;
-  std::mutex compute_mu_;  // one compute() at a time drives the slots and the pool
+  std::mutex compute_mu_;  // one batch at a time drives the slots and the pool
+  // flat combining of concurrent compute() calls: the caller that finds no leader becomes one and runs
+  // everything queued so far as ONE batch; the others sleep until their call is marked done
+  struct PendingCall {
+    const Input* in = nullptr;
+    int rc = 0;
+    std::string err;
+    bool done = false;
+  };
+  std::mutex comb_mu_;
+  std::condition_variable comb_cv_;
+  std::vector<PendingCall*> comb_queue_;
+  bool comb_leader_ = false;
   friend struct Batch;
 };
 

@@ -125,3 +125,35 @@ def test_monotone_in_base_quality(oracle):
     read_bases = b"ACGTACTTACGTACGT"  # one mismatch
     vals = [oracle.log10_double(rd(read_bases, q), hap) for q in (10, 20, 30, 40)]
     assert vals == sorted(vals, reverse=True)
+
+
+def test_independent_full_matrix_forward_at_realistic_size(oracle):
+    """An independently written forward algorithm (full (Lr+1)x(Lh+1) matrices in numpy float128 / longdouble,
+    column-vectorised, transition terms taken from the published formulas) agrees with the rolling-array C oracle
+    at HaplotypeCaller sizes, where the brute-force enumeration cannot go."""
+    rng = np.random.default_rng(12)
+    lib = oracle.load()
+    for Lr, Lh in ((150, 300), (97, 211), (250, 180)):
+        hap = rng.choice(list(b"ACGT"), Lh).astype(np.uint8)
+        s0 = int(rng.integers(0, max(1, Lh - Lr)))
+        rs = np.resize(hap[s0:], Lr).copy()
+        for k in rng.integers(0, Lr, 6):
+            rs[k] = int(rng.choice(list(b"ACGTN")))
+        q = rng.integers(6, 42, Lr); iq = rng.integers(20, 46, Lr); dq = rng.integers(20, 46, Lr); cq = rng.integers(8, 14, Lr)
+        LD = np.longdouble
+        ph = lambda v: LD(10.0) ** (-LD(v) / LD(10.0))  # noqa: E731
+        M = np.zeros((Lr + 1, Lh + 1), LD); X = np.zeros_like(M); Y = np.zeros_like(M)
+        Y[0, :] = LD(1.0) / LD(Lh)  # K = 1 here: the scale cancels in log10(S) - log10(K)
+        match = (rs[:, None] == hap[None, :]) | (rs[:, None] == ord("N")) | (hap[None, :] == ord("N"))
+        for r in range(1, Lr + 1):
+            e = ph(q[r - 1]); pGM = LD(1.0) - ph(cq[r - 1]); pXX = ph(cq[r - 1])
+            pMM = LD(lib.phmm_oracle_mm_d(int(iq[r - 1]), int(dq[r - 1])))  # the Jacobian-table value is part of the spec
+            prior = np.where(match[r - 1], LD(1.0) - e, e / LD(3.0))
+            M[r, 1:] = prior * (M[r - 1, :-1] * pMM + (X[r - 1, :-1] + Y[r - 1, :-1]) * pGM)
+            X[r, 1:] = M[r - 1, 1:] * ph(iq[r - 1]) + X[r - 1, 1:] * pXX
+            for c in range(1, Lh + 1):  # deletions chain along the row
+                Y[r, c] = M[r, c - 1] * ph(dq[r - 1]) + Y[r, c - 1] * pXX
+        want = float(np.log10((M[Lr, 1:] + X[Lr, 1:]).sum()))
+        read = (rs.tobytes(), q.astype(np.uint8).tobytes(), iq.astype(np.uint8).tobytes(), dq.astype(np.uint8).tobytes(), cq.astype(np.uint8).tobytes())
+        got = oracle.log10_double(read, hap.tobytes())
+        assert abs(got - want) < 1e-9, (Lr, Lh, got, want)

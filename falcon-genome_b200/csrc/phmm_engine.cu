@@ -53,22 +53,22 @@ static int64_t env_i64(const char* name, int64_t dflt) {
 }
 
 // class lookup by read length (hot in the planner: one lookup per read)
-static std::vector<const ClassRef*> g_f32_by_len[2];  // [ug]
+static std::vector<const ClassRef*> g_f32_by_len[3];  // [form]
 static std::vector<int16_t> g_qid_by_len;             // FP64 queue id
 static std::once_flag g_cls_once;
 static void build_len_tables() {
-  for (int ug = 0; ug < 2; ++ug) {
-    g_f32_by_len[ug].assign(1025, nullptr);
-    for (int len = 1; len <= 1024; ++len) g_f32_by_len[ug][len] = select_class(false, ug == 1, len);
+  for (int form = 0; form < 3; ++form) {
+    g_f32_by_len[form].assign(1025, nullptr);
+    for (int len = 1; len <= 1024; ++len) g_f32_by_len[form][len] = select_class(false, form, len);
   }
   g_qid_by_len.assign(1025, -1);
   for (int len = 1; len <= 1024; ++len)
     if (const ClassRef* k = select_class(true, false, len)) g_qid_by_len[len] = (int16_t)f64_queue_id(k->G, k->R);
 }
-static inline const ClassRef* f32_class_of_len(bool ug, int len) { return (len >= 1 && len <= 1024) ? g_f32_by_len[ug ? 1 : 0][len] : nullptr; }
+static inline const ClassRef* f32_class_of_len(int form, int len) { return (len >= 1 && len <= 1024) ? g_f32_by_len[form][len] : nullptr; }
 static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid_by_len[len] : -1; }
 
-// The value all gap-continuation quals of a read share (masked & 127 like the kernels), or -1.
+// The value all qualities of one plane of a read share (masked & 127 like the kernels), or -1.
 static int uniform_gcp(const uint8_t* c, int32_t len) {
   const uint8_t v = c[0] & 127u;
   const uint64_t vv = 0x0101010101010101ull * v, m7 = 0x7f7f7f7f7f7f7f7full;
@@ -308,7 +308,7 @@ struct Planner {
       if (force_min_g >= 0) min_G = force_min_g;
     }
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
-    std::vector<int> gcps;
+    std::vector<int> gcps, ukeys;
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
     int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
     size_t reads_bytes = 0, haps_bytes = 0;
@@ -327,6 +327,7 @@ struct Planner {
       if (!in.out(g)) return set_error(FCS_PHMM_EINVAL, "out_log10 is null");
       lens.resize(nr);
       gcps.resize(nr);
+      ukeys.resize(nr);
       hlens.resize(nh);
       uint64_t sum_r = 0, sum_h = 0;
       size_t rb = 0, hb = 0;
@@ -337,6 +338,13 @@ struct Planner {
         if (r.len > FCS_PHMM_MAX_READ_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "read longer than FCS_PHMM_MAX_READ_LEN");
         lens[i] = (uint32_t)r.len;
         gcps[i] = uniform_gcp(r.c, r.len);
+        // all-uniform key: continuation, insertion and deletion qualities constant over the read
+        ukeys[i] = -1;
+        if (gcps[i] >= 0) {
+          const int ui = uniform_gcp(r.i, r.len);
+          const int ud = ui >= 0 ? uniform_gcp(r.d, r.len) : -1;
+          if (ud >= 0) ukeys[i] = gcps[i] | (ui << 8) | (ud << 16);
+        }
         sum_r += (uint64_t)r.len;
         rb += 5u * round_up16((uint32_t)r.len);
       }
@@ -369,6 +377,7 @@ struct Planner {
       // columns.  Tasks are launched longest first, so the short ones fill the end of the grid and
       // the last wave of CTAs is half as long (equal-size tasks finish in lock step otherwise).
       static const int tail_pct = (int)env_i64("FCS_PHMM_TAIL_PCT", 25);
+      static const bool use_ua = env_i64("FCS_PHMM_NO_UA", 0) == 0;  // developer knob: disable the all-uniform kernels
       const uint32_t cols_limit =
           min_G ? 1u : ((k - first) * 100 >= (regions.size() - first) * (size_t)(100 - tail_pct) ? std::max(hs_cols / 2, 1u) : hs_cols);
       const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
@@ -391,12 +400,24 @@ struct Planner {
         const ClassRef* k0 = f32_class_of_len(false, (int)lens[ord[i]]);
         if (min_G) k0 = select_class_wide(false, false, (int)lens[ord[i]], min_G);
         else if (nr - i < 32 / k0->G) k0 = select_class_for(false, false, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
+        // All-uniform form: a full warp of reads that share one (continuation, insertion, deletion)
+        // quality triple.  Throughput policy only; leftover groups and latency-bound calls keep the
+        // wide-group classes of the other forms.
+        const ClassRef* ku = (!min_G && use_ua && ukeys[ord[i]] >= 0) ? f32_class_of_len(2, (int)lens[ord[i]]) : nullptr;
+        if (ku) {
+          const int ngu = 32 / ku->G;
+          if (nr - i < ngu) ku = nullptr;
+          for (int32_t x = 1; ku && x < ngu; ++x)
+            if (ukeys[ord[i + x]] != ukeys[ord[i]]) ku = nullptr;
+        }
+        if (ku) k0 = ku;
         const int NG = 32 / k0->G;
         const int cnt = std::min<int32_t>(NG, nr - i);
         int tg = gcps[ord[i]];  // uniform-GCP form only if every read of the task shares the value
         for (int32_t x = 1; x < cnt; ++x)
           if (gcps[ord[i + x]] != tg) tg = -1;
-        const ClassRef* kc = (tg >= 0 && k0->twin) ? k0->twin : k0;
+        const ClassRef* kc = ku ? ku : ((tg >= 0 && k0->twin) ? k0->twin : k0);
+        if (ku) tg = ukeys[ord[i]];
         TaskBucket* bk = nullptr;
         for (auto& b : s.buckets)
           if (b.tk == kc->tk && b.gcp == tg) { bk = &b; break; }
@@ -513,7 +534,7 @@ struct Planner {
       }
       F32Range r;
       r.tk = b.tk;
-      r.gcp = b.tk->ug ? b.gcp : -1;
+      r.gcp = b.tk->form ? b.gcp : -1;
       r.bucket = (uint32_t)bi;
       r.task0 = (uint32_t)P.n_tasks;
       r.n_tasks = (uint32_t)b.tasks.size();
@@ -736,12 +757,20 @@ void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) 
   p.hap_stage_bytes = 0;
   p.n_sym = P.n_sym;
   p.c_xx_f = 0.f; p.c_gm_f = 0.f; p.c_xx_d = 0.0; p.c_gm_d = 0.0;
+  p.c_mm_f = 0.f; p.c_mx_f = 0.f; p.c_my_f = 0.f;
 }
 
-// launch constants of a uniform-GCP launch, from the same tables the kernels index
-static void set_gcp_constants(KParams& p, int gcp) {
-  if (gcp < 0) return;
+// launch constants of a uniform-GCP / all-uniform launch, from the same tables the kernels index.
+// key = gcp | ins << 8 | del << 16 (the insertion / deletion bytes matter to the all-uniform form only)
+static void set_gcp_constants(KParams& p, int key) {
+  if (key < 0) return;
   const Luts& L = luts();
+  const int gcp = key & 127;
+  const uint32_t iq = (uint32_t)(key >> 8) & 127u, dq = (uint32_t)(key >> 16) & 127u;
+  const uint32_t mn = std::min(iq, dq), mx = std::max(iq, dq);
+  p.c_mm_f = L.mm_f[((mx * (mx + 1u)) >> 1) + mn];
+  p.c_mx_f = L.ph2pr_f[iq];
+  p.c_my_f = L.ph2pr_f[dq];
   p.c_xx_f = L.ph2pr_f[gcp & 127];
   p.c_gm_f = 1.0f - p.c_xx_f;
   p.c_xx_d = L.ph2pr_d[gcp & 127];
@@ -827,8 +856,8 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
           swept += 32.0 * cd.R * cols;
           useful += rl * hl;
         }
-        fprintf(stderr, "[fcs_phmm] f32 launch tier %d ug %d gcp %d tasks %u smem %zu hs_cap %u stage %u geom_eff %.3f classes%s\n", r.tk->tier,
-                (int)r.tk->ug, r.gcp, r.n_tasks, r.smem, r.hs_cap, r.hap_stage, useful / swept, cl.c_str());
+        fprintf(stderr, "[fcs_phmm] f32 launch tier %d form %d key 0x%x tasks %u smem %zu hs_cap %u stage %u geom_eff %.3f classes%s\n", r.tk->tier,
+                r.tk->form, (unsigned)r.gcp, r.n_tasks, r.smem, r.hs_cap, r.hap_stage, useful / swept, cl.c_str());
       }
       CK(r.tk->launch(p, r.n_tasks, r.smem + smem_pad, pick(li++, nl)));
       stats_.launches += 1;
@@ -851,7 +880,7 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
       fill_kparams(d, s, p, true);
       p.hs_cap = r.hs_cap;
       p.hap_stage_bytes = r.hap_stage;
-      set_gcp_constants(p, r.tk->ug ? P.f64_gcp : -1);
+      set_gcp_constants(p, r.tk->form ? P.f64_gcp : -1);
       if (r.smem > 227 * 1024)
         return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype too long for the FP64 kernel's shared memory (" + std::to_string(r.smem) + " bytes)");
       const unsigned resident = (unsigned)d.sm_count * (unsigned)std::max(1, r.tk->min_blocks);

@@ -48,11 +48,11 @@ struct F32Range {
   const TierKernel* tk;
   uint32_t task0, n_tasks, hs_cap, hap_stage;
   uint32_t bucket;  // index of the TaskBucket the tasks come from
-  int gcp;          // >= 0: uniform-GCP launch with this quality, -1: general form
+  int gcp;          // >= 0: uniform launch: gcp | ins << 8 | del << 16 (ins / del for the all-uniform form), -1: general form
   size_t smem;      // dynamic shared memory: max over the classes present
   uint32_t max_task_cost;
 };
-// Tasks of one launch: one tier kernel x one gap-continuation value (or -1 = general form).
+// Tasks of one launch: one tier kernel x one uniform-quality key (or -1 = general form).
 struct TaskBucket {
   const TierKernel* tk = nullptr;
   int gcp = -1;

@@ -115,17 +115,18 @@ __device__ __forceinline__ int base_code(uint32_t b) {
 //   union = { ph2pr LUT + read staging }  (needed until the tile is built)
 //         = { haplotype stream }          (written after the tile is built)
 // The N symbol row exists only if a haplotype of the launch contains an N (n_sym = 6).  Together
-// these keep the common 150-bp class at 12 one-warp CTAs per SM.
-template <typename T, int G, int R, bool LIST>
+// these keep the common 150-bp class at 12 one-warp CTAs per SM (8 for the all-uniform G=4, R=38 class,
+// whose table alone is 24 KB).
+template <typename T, int G, int R, bool LIST, int FORM = 0>
 struct Layout {
   static constexpr int NG = 32 / G;
   static constexpr int ROWS = G * R;
-  static constexpr int STRIDE = tab_stride_bytes(R, (int)sizeof(T));
+  static constexpr int STRIDE = tab_stride_form(R, (int)sizeof(T), FORM);
   static constexpr int SYM_PITCH = 32 * STRIDE;     // bytes between symbol rows of the table
   static constexpr int HSCALE = SYM_PITCH / 16;     // value stored in the haplotype stream per symbol
-  static constexpr int NV = (R * (int)sizeof(T) + 15) / 16;  // LDS.128 per step
-  static constexpr int VW = 16 / (int)sizeof(T);    // values per LDS.128
-  static constexpr int RSTAGE = 5 * (int)round_up16(ROWS);   // read staging bytes per group
+  // read staging bytes per group; the all-uniform form reads bases and base qualities straight from
+  // global memory when it builds its tile, so it stages nothing
+  static constexpr int RSTAGE = FORM == 2 ? 0 : 5 * (int)round_up16(ROWS);
   static constexpr int OFF_BAR = 0;
   static constexpr int OFF_TAB = 128;
   static constexpr int LUT_BYTES = 128 * (int)sizeof(T);
@@ -145,7 +146,7 @@ struct Layout {
 // ----------------------------------------------------------------------------------------
 // the register tile of one lane and its wavefront loop
 //
-// UG ("uniform GCP"): every read of the launch has one constant gap-continuation quality
+// FORM 1, UG ("uniform GCP"): every read of the launch has one constant gap-continuation quality
 // (GATK HaplotypeCaller / Mutect2 always pass a constant 10 [upstream, SURVEY A.6]).  Then
 // pXX = pYY = ph2pr[gcp] and pGM = 1 - pXX are launch constants that the FMAs take from the
 // constant bank instead of the register file.  The register file feeds about two 32-bit
@@ -153,33 +154,57 @@ struct Layout {
 // operand reads per cell, not the issue slots, bound this kernel: 20 reads/cell in the general
 // form, 17 with UG (and 7 instead of 8 registers per row).  Only the Y update keeps a per-row
 // multiplier (pYY[k] = 1 on the rows above the read, so their Y stays K/Lh).
-template <typename T, int G, int R, bool UG>
+//
+// FORM 2, UA ("uniform all"): the insertion and deletion qualities are constant over the reads of
+// the launch as well (GATK without the PCR indel model, i.e. PCR-free libraries: 45/45; BASELINE
+// config 2).  Then pMM, pMX and pMY are launch constants too: 14 register operands per cell and 4
+// registers per row (M, X, Y, pYY), which lets a lane hold up to 38 rows -- a 150-bp read on FOUR
+// lanes, eight reads per warp, half the wavefront skew.  The rows above the read need no per-row
+// zeros here: their prior is 0, so M = 0; X of tile row 0 is forced to 0 by its own register pair
+// (pXX[0], pMX[0]) and every X below it is fma(0, cXX, 0 * cMX) = 0; Y keeps pYY[k] = 1.
+template <typename T, int G, int R, int FORM>
 struct Tile {
   using A = Ar<T>;
-  static constexpr int STRIDE = tab_stride_bytes(R, (int)sizeof(T));
+  static constexpr bool UG = FORM >= 1, UA = FORM == 2;
+  static constexpr int STRIDE = tab_stride_form(R, (int)sizeof(T), FORM);
+  static constexpr bool ROT = tab_rotated(R, (int)sizeof(T), FORM);  // rotated table rows, see tab_stride_form
   static constexpr int NV = (R * (int)sizeof(T) + 15) / 16;
   static constexpr int VW = 16 / (int)sizeof(T);
+  // steps per loop trip: the unrolled body should stay near 650 instructions (instruction cache)
+  static constexpr int UNROLL = (R > 24) ? 2 : kUnrollT;
   static constexpr int RG = UG ? 1 : R;  // rows that keep their own pGM / pXX
+  static constexpr int RA = UA ? 1 : R;  // rows that keep their own pMM / pMX / pMY
 
-  T pMM[R], pMX[R], pMY[R];
+  T pMM[RA], pMX[RA], pMY[RA];  // UA: pMX[0] only (X-from-M multiplier of tile row 0)
   T pGM[RG], pXX[RG];  // general form: per row.  UG: [0] only (pXX[0] = X multiplier of tile row 0)
   T pYY[UG ? R : 1];   // UG: per-row Y multiplier.  general: [0] = Y multiplier of tile row 0
   T cXX, cGM;          // UG: launch constants
-  uint32_t padmask;    // bit k: row k of this lane lies above the read
+  T cMM, cMX, cMY;     // UA: launch constants
+  int npl;             // rows of this lane that lie above the read (always its first rows)
+  int off_last;        // ROT: byte offset of this lane's last 16-byte chunk from its (rotated) row base
+
+  // this lane's row base inside a symbol row of the table, and the offset of chunk v from it
+  static __device__ __forceinline__ int lane_base(int lane) { return lane * STRIDE + (ROT ? ((lane >> 2) & 1) * 16 : 0); }
+  __device__ __forceinline__ int chunk_off(int v) const { return (ROT && v == NV - 1) ? off_last : v * 16; }
 
   __device__ __forceinline__ T gm(int k) const { return UG ? cGM : pGM[UG ? 0 : k]; }
   __device__ __forceinline__ T xx(int k) const { return UG ? (k == 0 ? pXX[0] : cXX) : pXX[UG ? 0 : k]; }
   __device__ __forceinline__ T yy(int k) const { return UG ? pYY[UG ? k : 0] : (k == 0 ? pYY[0] : pXX[UG ? 0 : k]); }
+  __device__ __forceinline__ T mm_(int k) const { return UA ? cMM : pMM[UA ? 0 : k]; }
+  __device__ __forceinline__ T mx(int k) const { return UA ? (k == 0 ? pMX[0] : cMX) : pMX[UA ? 0 : k]; }
+  __device__ __forceinline__ T my(int k) const { return UA ? cMY : pMY[UA ? 0 : k]; }
 
   // Fill constants and this lane's slice of the prior table from the staged read.
-  // rs points at the group's staged read blob (planes of Lp bytes); len == 0 => no read.
+  // tab_lane = table base + lane_base(lane).  rs points at the group's read blob (planes of Lp bytes; staged in shared memory, or in global
+  // memory for the UA form, which touches only bases and base qualities); len == 0 => no read.
   // row0 / npad: tile row 0 of lane 0 is row `row0` of a striped read whose first `npad` rows are
   // boundary replicas (single pass: row0 = 0, npad = G*R - len).
   __device__ __forceinline__ void build(const uint8_t* rs, uint32_t len, int lig, const T* lut, const T* __restrict__ mm,
                                         uint8_t* tab_lane, bool with_n, int row0 = 0, int npad_override = -1) {
     const uint32_t Lp = round_up16(len);
     const int npad = (npad_override >= 0 ? npad_override : G * R - (int)len) - row0;
-    padmask = 0;
+    npl = min(max(npad - lig * R, 0), R);
+    off_last = ((threadIdx.x >> 2) & 1) ? -16 : (NV - 1) * 16;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int pos = lig * R + k - npad;
@@ -188,28 +213,33 @@ struct Tile {
       T xxk, yyk, gmk;
       if (pos >= 0) {
         const uint32_t b = rs[pos];
-        const uint32_t q = rs[Lp + pos] & 127u, iq = rs[2 * Lp + pos] & 127u, dq = rs[3 * Lp + pos] & 127u,
-                       cq = rs[4 * Lp + pos] & 127u;
+        const uint32_t q = rs[Lp + pos] & 127u;
         const T e = lut[q];
         pm = A::sub(T(1), e);
         px = A::div(e, T(3));
-        const uint32_t mn = min(iq, dq), mx = max(iq, dq);
-        pMM[k] = mm[((mx * (mx + 1u)) >> 1) + mn];
-        const T pc = UG ? cXX : lut[cq];
+        if constexpr (!UA) {
+          const uint32_t iq = rs[2 * Lp + pos] & 127u, dq = rs[3 * Lp + pos] & 127u;
+          const uint32_t mn = min(iq, dq), mx = max(iq, dq);
+          pMM[k] = mm[((mx * (mx + 1u)) >> 1) + mn];
+          pMX[k] = lut[iq];
+          pMY[k] = lut[dq];
+        } else if (k == 0) {
+          pMX[0] = cMX;
+        }
+        T pc = cXX;
+        if constexpr (!UG) pc = lut[rs[4 * Lp + pos] & 127u];
         gmk = A::sub(T(1), pc);
-        pMX[k] = lut[iq];
-        pMY[k] = lut[dq];
         xxk = pc;
         yyk = pc;
         rcode = base_code(b);
       } else {
         // boundary replica: M = 0 (prior 0), X = 0, Y stays K/Lh.  Tile row 0 forces X to 0 whatever
         // the shuffle delivers; below it X_up is already 0.
-        pMM[k] = T(0); pMX[k] = T(0); pMY[k] = T(0);
+        if constexpr (!UA) { pMM[k] = T(0); pMX[k] = T(0); pMY[k] = T(0); }
+        else if (k == 0) pMX[0] = T(0);
         gmk = T(0);
         xxk = (k == 0) ? T(0) : T(1);
         yyk = T(1);
-        padmask |= 1u << k;
       }
       if constexpr (UG) {
         pYY[k] = yyk;
@@ -219,14 +249,15 @@ struct Tile {
         pXX[k] = (k == 0) ? xxk : ((pos >= 0) ? xxk : T(1));
         if (k == 0) pYY[0] = yyk;
       }
+      const int koff = chunk_off(k / VW) + (k % VW) * (int)sizeof(T);
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
         const bool m = (rcode == kCodeN) || (rcode == h);
         const T v = (pos >= 0) ? (m ? pm : px) : T(0);
-        *reinterpret_cast<T*>(tab_lane + h * (32 * STRIDE) + k * (int)sizeof(T)) = v;
+        *reinterpret_cast<T*>(tab_lane + h * (32 * STRIDE) + koff) = v;
       }
-      *reinterpret_cast<T*>(tab_lane + kCodePad * (32 * STRIDE) + k * (int)sizeof(T)) = T(0);
-      if (with_n) *reinterpret_cast<T*>(tab_lane + kCodeN * (32 * STRIDE) + k * (int)sizeof(T)) = (pos >= 0) ? pm : T(0);
+      *reinterpret_cast<T*>(tab_lane + kCodePad * (32 * STRIDE) + koff) = T(0);
+      if (with_n) *reinterpret_cast<T*>(tab_lane + kCodeN * (32 * STRIDE) + koff) = (pos >= 0) ? pm : T(0);
     }
   }
 
@@ -243,7 +274,7 @@ struct Tile {
     for (int k = 0; k < R; ++k) {
       st.M[k] = T(0);
       st.X[k] = T(0);
-      st.Y[k] = ((padmask >> k) & 1u) ? y_init : T(0);
+      st.Y[k] = (k < npl) ? y_init : T(0);
     }
     st.dM = T(0);
     st.dX = T(0);
@@ -258,7 +289,7 @@ struct Tile {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       if constexpr (sizeof(T) == 4) {
-        const float4 f = *reinterpret_cast<const float4*>(prow + v * 16);
+        const float4 f = *reinterpret_cast<const float4*>(prow + chunk_off(v));
         pr[v * 4 + 0] = f.x; pr[v * 4 + 1] = f.y; pr[v * 4 + 2] = f.z; pr[v * 4 + 3] = f.w;
       } else {
         const double2 f = *reinterpret_cast<const double2*>(prow + v * 16);
@@ -271,15 +302,15 @@ struct Tile {
       const T md = k ? st.M[k - 1] : st.dM;
       const T xd = k ? st.X[k - 1] : st.dX;
       const T yd = k ? st.Y[k - 1] : st.dY;
-      T s = A::mul(md, pMM[k]);
+      T s = A::mul(md, mm_(k));
       s = A::fma(xd, gm(k), s);
       s = A::fma(yd, gm(k), s);
       nM[k] = A::mul(s, pr[k]);
-      nY[k] = A::fma(st.Y[k], yy(k), A::mul(st.M[k], pMY[k]));
+      nY[k] = A::fma(st.Y[k], yy(k), A::mul(st.M[k], my(k)));
     }
-    nX[0] = A::fma(uX, xx(0), A::mul(uM, pMX[0]));
+    nX[0] = A::fma(uX, xx(0), A::mul(uM, mx(0)));
 #pragma unroll
-    for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), A::mul(nM[k - 1], pMX[k]));
+    for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), A::mul(nM[k - 1], mx(k)));
     st.acc = A::add(st.acc, A::add(nM[R - 1], nX[R - 1]));
     st.dM = uM; st.dX = uX; st.dY = uY;
 #pragma unroll
@@ -291,7 +322,7 @@ struct Tile {
   __device__ __forceinline__ T run(const uint8_t* tab_lane, const uint16_t* hs_lane, int nsteps, T y_init) const {
     State st;
     init(st, y_init);
-#pragma unroll(kUnrollT)
+#pragma unroll(UNROLL)
     for (int t = 0; t < nsteps; ++t) {
       const uint32_t hoff = hs_lane[t];
       const T uM = __shfl_up_sync(0xffffffffu, st.M[R - 1], 1, G);
@@ -333,14 +364,15 @@ __device__ __forceinline__ void emit_f64(const KParams& p, const ReadMeta& rm, u
 // ----------------------------------------------------------------------------------------
 // Task form (FP32 main path): one CTA = one task = <= 32/G reads of a region x a run of its
 // haplotypes, all lane groups streaming the same haplotypes.
-template <typename T, int G, int R, bool UG>
+template <typename T, int G, int R, int FORM>
 __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint8_t* smem) {
-  using L = Layout<T, G, R, false>;
+  using L = Layout<T, G, R, false, FORM>;
+  constexpr bool UA = FORM == 2;
   using A = Ar<T>;
   const int lane = threadIdx.x;
   const int grp = lane / G, lig = lane % G;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint8_t* tab_lane = smem + L::OFF_TAB + lane * L::STRIDE;
+  uint8_t* tab_lane = smem + L::OFF_TAB + Tile<T, G, R, FORM>::lane_base(lane);
   uint8_t* un = smem + L::off_union(p.n_sym);
   T* lut = reinterpret_cast<T*>(un);
   uint8_t* rstage = un + L::LUT_BYTES + grp * L::RSTAGE;
@@ -351,9 +383,9 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
-  Tile<T, G, R, UG> tile;
-  if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; }
-  else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; }
+  Tile<T, G, R, FORM> tile;
+  if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; tile.cMM = p.c_mm_f; tile.cMX = p.c_mx_f; tile.cMY = p.c_my_f; }
+  else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; tile.cMM = T(0); tile.cMX = T(0); tile.cMY = T(0); }
 
   const bool active = grp < (int)task.n_reads;
   const uint32_t read = task.read0 + (active ? grp : 0);
@@ -363,15 +395,16 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   const HapMeta h_last = p.hmeta[task.hap0 + task.n_haps - 1];
   const uint32_t hap_bytes = (h_last.data_off16 - h_first.data_off16) * 16u + round_up16(h_last.len);
   // ---- stage reads + haplotypes with TMA bulk copies
-  const uint32_t my_bytes = ((active && lig == 0) ? 5u * round_up16(rlen) : 0u) + (lane == 0 ? hap_bytes : 0u);
+  const uint32_t my_bytes = ((!UA && active && lig == 0) ? 5u * round_up16(rlen) : 0u) + (lane == 0 ? hap_bytes : 0u);
   const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
   if (lane == 0) mbar_expect_tx(bar, tot);
   __syncwarp();
-  if (active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
+  if (!UA && active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
   if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
+  // ---- per-row constants + prior table (the UA form builds from global memory while the copy flies)
+  if constexpr (UA) tile.build(p.reads + (size_t)rm.data_off16 * 16u, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
   mbar_wait(bar, 0u);
-  // ---- per-row constants + prior table
-  tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+  if constexpr (!UA) tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
   __syncwarp();  // every lane is done with the LUT and the read staging before the stream overwrites them
   // ---- haplotype stream: [G-1 PAD] hap0 [G-1 PAD] hap1 ... [G-1 PAD]
   uint32_t off = 0;
@@ -403,15 +436,16 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
 }
 
 // Queue form (FP64 rerun): CTA `cta` of `nctas` grid-strides over queue `qid`, one pair per lane group.
-template <typename T, int G, int R, bool UG>
+template <typename T, int G, int R, int FORM>
 __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32_t cta, uint32_t nctas, uint8_t* smem) {
-  using L = Layout<T, G, R, true>;
+  static_assert(FORM != 2, "the all-uniform form has no queue kernel");
+  using L = Layout<T, G, R, true, FORM>;
   using A = Ar<T>;
   constexpr int NG = L::NG;
   const int lane = threadIdx.x;
   const int grp = lane / G, lig = lane % G;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint8_t* tab_lane = smem + L::OFF_TAB + lane * L::STRIDE;
+  uint8_t* tab_lane = smem + L::OFF_TAB + Tile<T, G, R, FORM>::lane_base(lane);
   uint8_t* un = smem + L::off_union(p.n_sym);
   T* lut = reinterpret_cast<T*>(un);
   uint8_t* rstage = un + L::LUT_BYTES + grp * L::RSTAGE;
@@ -426,9 +460,10 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
   uint32_t parity = 0;
-  Tile<T, G, R, UG> tile;
+  Tile<T, G, R, FORM> tile;
   if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; }
   else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; }
+  tile.cMM = T(0); tile.cMX = T(0); tile.cMY = T(0);
   const RerunEntry* list = p.rerun + p.rerun_base[qid];
   for (uint32_t base = cta * NG; base < count; base += nctas * NG) {
     const bool active = base + grp < count;

@@ -9,16 +9,18 @@
 
 namespace fcsphmm {
 
-extern const TierKernel kTierF32T0, kTierF32T1, kTierF32T2, kTierF32UT0, kTierF32UT1, kTierF32UT2;
+extern const TierKernel kTierF32T0, kTierF32T1, kTierF32T2, kTierF32UT0, kTierF32UT1, kTierF32UT2, kTierF32AT1, kTierF32AT2;
 extern const TierKernel kTierF64T0, kTierF64T1, kTierF64T2, kTierF64UT0, kTierF64UT1, kTierF64UT2;
 
 namespace {
-const TierKernel* g_kernels[] = {&kTierF32T0, &kTierF32T1, &kTierF32T2, &kTierF32UT0, &kTierF32UT1, &kTierF32UT2,
+const TierKernel* g_kernels[] = {&kTierF32T0, &kTierF32T1, &kTierF32T2, &kTierF32UT0, &kTierF32UT1, &kTierF32UT2, &kTierF32AT1, &kTierF32AT2,
                                  &kTierF64T0, &kTierF64T1, &kTierF64T2, &kTierF64UT0, &kTierF64UT1, &kTierF64UT2};
-constexpr int kNumKernels = 12;
+constexpr int kNumKernels = 14;
+constexpr int kForms = 3;  // general, uniform-GCP, all-uniform
+inline int fidx(bool f64, int form) { return (f64 ? kForms : 0) + form; }
 constexpr int kMaxSelLen = 1024;
-std::vector<ClassRef> g_classes[4];             // [f64 * 2 + ug]
-std::vector<const ClassRef*> g_sel[4];          // by read length
+std::vector<ClassRef> g_classes[2 * kForms];    // [fidx(f64, form)]
+std::vector<const ClassRef*> g_sel[2 * kForms];  // by read length
 std::vector<std::pair<int, int>> g_f64_queues;  // (G, R) of the general-form FP64 classes
 std::once_flag g_once;
 
@@ -36,27 +38,29 @@ double class_cost(bool f64, int G, int R) { return step_cost(f64, R) * G * (1.0 
 void build() {
   for (int i = 0; i < kNumKernels; ++i) {
     const TierKernel* tk = g_kernels[i];
-    auto& v = g_classes[(tk->f64 ? 2 : 0) + (tk->ug ? 1 : 0)];
+    auto& v = g_classes[fidx(tk->f64, tk->form)];
     for (int c = 0; c < tk->n_classes; ++c) v.push_back(ClassRef{tk, c, tk->classes[c].G, tk->classes[c].R, nullptr});
   }
-  for (int f = 0; f < 4; ++f) {
+  for (int f = 0; f < 2 * kForms; ++f) {
     g_sel[f].assign(kMaxSelLen + 1, nullptr);
     for (int len = 1; len <= kMaxSelLen; ++len) {
       const ClassRef* best = nullptr;
       double bc = 0;
       for (const ClassRef& k : g_classes[f]) {
         if (k.G * k.R < len + 1) continue;
-        const double c = class_cost(f >= 2, k.G, k.R);
+        const double c = class_cost(f >= kForms, k.G, k.R);
         if (!best || c < bc) { best = &k; bc = c; }
       }
       g_sel[f][len] = best;
     }
   }
-  for (const ClassRef& k : g_classes[2]) g_f64_queues.emplace_back(k.G, k.R);
-  for (int f = 0; f < 4; ++f)
+  for (const ClassRef& k : g_classes[fidx(true, 0)]) g_f64_queues.emplace_back(k.G, k.R);
+  for (int f = 0; f < 2 * kForms; ++f) {
+    if (f % kForms == 2) continue;  // the all-uniform form has its own class list, no twin
     for (ClassRef& k : g_classes[f])
-      for (const ClassRef& o : g_classes[f ^ 1])
+      for (const ClassRef& o : g_classes[f - f % kForms + (1 - f % kForms)])
         if (o.G == k.G && o.R == k.R) { k.twin = &o; break; }
+  }
 }
 }  // namespace
 
@@ -66,29 +70,29 @@ const TierKernel* const* tier_kernels(int* n) {
   return g_kernels;
 }
 
-const ClassRef* select_class(bool f64, bool ug, int read_len) {
+const ClassRef* select_class(bool f64, int form, int read_len) {
   std::call_once(g_once, build);
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
-  return g_sel[(f64 ? 2 : 0) + (ug ? 1 : 0)][read_len];
+  return g_sel[fidx(f64, form)][read_len];
 }
 
-const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, int avg_hap_len) {
+const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, int avg_hap_len) {
   std::call_once(g_once, build);
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
   // memo: the choice depends on the haplotype length only weakly -> four length bins; benign races
   // (every thread computes the same pointer)
-  static std::atomic<const ClassRef*> memo[4][kMaxSelLen + 1][8][4];
+  static std::atomic<const ClassRef*> memo[2 * kForms][kMaxSelLen + 1][8][4];
   const int nb = n_reads < 1 ? 1 : (n_reads > 7 ? 7 : n_reads);
   const int hb = avg_hap_len < 150 ? 0 : (avg_hap_len < 300 ? 1 : (avg_hap_len < 600 ? 2 : 3));
   static const int hb_len[4] = {100, 220, 420, 900};
-  std::atomic<const ClassRef*>& slot = memo[(f64 ? 2 : 0) + (ug ? 1 : 0)][read_len][nb][hb];
+  std::atomic<const ClassRef*>& slot = memo[fidx(f64, form)][read_len][nb][hb];
   if (const ClassRef* hit = slot.load(std::memory_order_relaxed)) return hit;
   n_reads = nb;
   avg_hap_len = hb_len[hb];
   const ClassRef* best = nullptr;
   double bc = 0;
   const double lh = avg_hap_len > 0 ? avg_hap_len : 300;
-  for (const ClassRef& k : g_classes[(f64 ? 2 : 0) + (ug ? 1 : 0)]) {
+  for (const ClassRef& k : g_classes[fidx(f64, form)]) {
     if (k.G * k.R < read_len + 1) continue;
     const int served = std::min(n_reads, 32 / k.G);
     const double c = step_cost(f64, k.R) * (lh + k.G - 1) / served;
@@ -98,21 +102,21 @@ const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, i
   return best;
 }
 
-const ClassRef* select_class_wide(bool f64, bool ug, int read_len, int min_G) {
+const ClassRef* select_class_wide(bool f64, int form, int read_len, int min_G) {
   std::call_once(g_once, build);
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
   const ClassRef* best = nullptr;
-  for (const ClassRef& k : g_classes[(f64 ? 2 : 0) + (ug ? 1 : 0)]) {
+  for (const ClassRef& k : g_classes[fidx(f64, form)]) {
     if (k.G * k.R < read_len + 1 || k.G < min_G) continue;
     // fewest rows per lane first (shortest dependent chain per step), then fewest lanes
     if (!best || k.R < best->R || (k.R == best->R && k.G < best->G)) best = &k;
   }
-  return best ? best : select_class(f64, ug, read_len);
+  return best ? best : select_class(f64, form, read_len);
 }
 
-const ClassRef* find_class(bool f64, bool ug, int G, int R) {
+const ClassRef* find_class(bool f64, int form, int G, int R) {
   std::call_once(g_once, build);
-  for (const ClassRef& k : g_classes[(f64 ? 2 : 0) + (ug ? 1 : 0)])
+  for (const ClassRef& k : g_classes[fidx(f64, form)])
     if (k.G == G && k.R == R) return &k;
   return nullptr;
 }
@@ -129,9 +133,9 @@ int f64_queue_id(int G, int R) {
   return -1;
 }
 
-const ClassRef* f64_queue_class(int qid, bool ug) {
+const ClassRef* f64_queue_class(int qid, int form) {
   std::call_once(g_once, build);
-  return find_class(true, ug, g_f64_queues[qid].first, g_f64_queues[qid].second);
+  return find_class(true, form, g_f64_queues[qid].first, g_f64_queues[qid].second);
 }
 
 }  // namespace fcsphmm

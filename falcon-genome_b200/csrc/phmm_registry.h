@@ -1,4 +1,4 @@
-// phmm_registry.h — the compiled kernels: one per (precision, GCP form, register tier), each
+// phmm_registry.h — the compiled kernels: one per (precision, form, register tier), each
 // holding several (lanes per read G, rows per lane R) classes (phmm_tiers.h).
 #pragma once
 #include <cuda_runtime.h>
@@ -16,7 +16,8 @@ struct ClassDesc {
 
 struct TierKernel {
   bool f64;        // double-precision, queue-driven rerun kernel
-  bool ug;         // uniform gap-continuation quality: pGM / pXX come from the constant bank
+  int form;        // 0 general; 1 uniform gap-continuation quality (pGM / pXX from the constant bank);
+                   // 2 all-uniform (pMM / pMX / pMY as well; FP32 only)
   int tier;        // 0: 16 CTAs/SM (<=128 regs), 1: 12 (<=168), 2: 8 (<=255)
   int min_blocks;  // __launch_bounds__ residency target (one-warp CTAs per SM)
   int n_classes;
@@ -33,22 +34,22 @@ struct ClassRef {
   size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage, uint32_t n_sym) const { return tk->classes[cls].smem_bytes(hs_cap, hap_stage, n_sym); }
 };
 
-// All compiled kernels (12), terminated by launch == nullptr.
+// All compiled kernels (14).
 const TierKernel* const* tier_kernels(int* n);
 // Cheapest class covering a read of this length (rows needed = len + 1) when every lane group of the
 // warp is filled, or nullptr.
-const ClassRef* select_class(bool f64, bool ug, int read_len);
+const ClassRef* select_class(bool f64, int form, int read_len);
 // Cheapest class per read served when only n_reads (>= 1) reads are left to fill the 32/G lane groups
 // against haplotypes of about avg_hap_len columns: favours wide groups (large G, small R) for leftovers.
-const ClassRef* select_class_for(bool f64, bool ug, int read_len, int n_reads, int avg_hap_len);
-const ClassRef* find_class(bool f64, bool ug, int G, int R);
+const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, int avg_hap_len);
+const ClassRef* find_class(bool f64, int form, int G, int R);
 // Latency policy (under-filled calls): the class with at least min_G lanes per read and the fewest rows
 // per lane that covers the read -- the shortest serial chain per haplotype column.
-const ClassRef* select_class_wide(bool f64, bool ug, int read_len, int min_G);
+const ClassRef* select_class_wide(bool f64, int form, int read_len, int min_G);
 // FP64 rerun queues are keyed by the (G, R) of the general-form FP64 class of the read.
 int f64_queue_count();
 int f64_queue_id(int G, int R);
-const ClassRef* f64_queue_class(int qid, bool ug);
+const ClassRef* f64_queue_class(int qid, int form);
 
 constexpr int kTierMinBlocks[3] = {16, 12, 8};
 

@@ -90,6 +90,8 @@ struct KParams {
   // uniform-GCP launches: ph2pr[gcp] and 1 - ph2pr[gcp], read from the constant bank
   float c_xx_f, c_gm_f;
   double c_xx_d, c_gm_d;
+  // all-uniform launches (FP32 only): matchToMatch[ins, del], ph2pr[ins], ph2pr[del]
+  float c_mm_f, c_mx_f, c_my_f;
 };
 
 PHMM_HD inline constexpr uint32_t round_up16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -100,6 +102,20 @@ PHMM_HD inline constexpr int tab_stride_bytes(int R, int esz) {
   int n16 = (R * esz + 15) / 16;
   if ((n16 & 1) == 0) n16 += 1;
   return n16 * 16;
+}
+
+// Kernel forms: 0 = general, 1 = uniform gap-continuation quality, 2 = all transition qualities uniform.
+// The FP32 all-uniform form holds up to 38 rows per lane, so its prior table (5 symbols x 32 lanes x
+// stride) decides how many CTAs share an SM; padding the stride to an odd multiple of 16 B would cost
+// one CTA per SM for R = 37..40.  When the stride is 2 (mod 4) sixteen-byte chunks it stays unpadded
+// and the table is ROTATED instead: lanes 4..7 of every quarter-warp keep their chunks one position
+// further (the last chunk wraps to the front), which makes the eight lanes of an LDS.128 phase hit
+// eight distinct bank groups again.
+PHMM_HD inline constexpr bool tab_rotated(int R, int esz, int form) {
+  return form == 2 && esz == 4 && (((R * esz + 15) / 16) % 4) == 2;
+}
+PHMM_HD inline constexpr int tab_stride_form(int R, int esz, int form) {
+  return tab_rotated(R, esz, form) ? ((R * esz + 15) / 16) * 16 : tab_stride_bytes(R, esz);
 }
 
 }  // namespace fcsphmm

@@ -136,6 +136,63 @@ def test_every_read_length_class(hmm, oracle):
     check_against_oracle(oracle, b, out, used, raw, simd=False)
 
 
+def _uniform_indel_region(rng, L, n_reads, hap, ins=45, dele=45, gcp=10, n_rate=0.0):
+    reads = []
+    for _ in range(n_reads):
+        s = int(rng.integers(0, max(1, len(hap) - L)))
+        bases = bytearray((hap + hap + hap + hap)[s:s + L])
+        for x in range(L):
+            u = rng.random()
+            if u < 0.02:
+                bases[x] = int(rng.choice(list(b"ACGT")))
+            elif u < 0.02 + n_rate:
+                bases[x] = ord("N")
+        q = bytes(rng.integers(6, 42, L).astype(np.uint8))
+        reads.append((bytes(bases), q, bytes([ins]) * L, bytes([dele]) * L, bytes([gcp]) * L))
+    return reads
+
+
+def test_all_uniform_form_every_tile(hmm, oracle):
+    """Reads whose insertion / deletion / continuation qualities are constant take the all-uniform
+    kernels (G=4 up to 151 rows, G=8 up to 303): sweep every rows-per-lane class with full warps,
+    exact tile fits, several quality triples in one call, N bases in reads and haplotypes, and
+    groups that mix eligible and non-eligible reads (those must fall back to the other forms)."""
+    rng = np.random.default_rng(2024)
+    hap = bytes(rng.choice(list(b"ACGT"), 341).astype(np.uint8))
+    hap_n = bytearray(hap[20:300]); hap_n[57] = ord("N"); hap_n[200] = ord("N")
+    regs = []
+    lens = [1, 3, 7, 8, 15, 16, 31, 39, 40, 47, 63, 64, 79, 80, 87, 88, 100, 103, 104, 111, 119, 120, 127, 135, 136, 143, 144,
+            150, 151, 152, 159, 160, 167, 168, 175, 183, 184, 199, 200, 215, 216, 231, 239, 240, 250, 255, 256, 271, 287, 288,
+            295, 296, 302, 303, 304, 320]
+    for n, L in enumerate(lens):
+        trip = [(45, 45, 10), (40, 30, 10), (45, 45, 12), (20, 45, 3)][n % 4]
+        reads = _uniform_indel_region(rng, L, 8 if L < 152 else 4, hap, *trip, n_rate=0.01 if n % 5 == 0 else 0.0)
+        haps = [hap, hap[:120], hap[33:]] + ([bytes(hap_n)] if n % 3 == 0 else [])
+        regs.append(Region(reads, haps))
+    # one region with two quality triples (sorted by length they interleave), one with a non-uniform read
+    mixed = _uniform_indel_region(rng, 150, 9, hap, 45, 45, 10) + _uniform_indel_region(rng, 150, 9, hap, 44, 45, 10)
+    regs.append(Region(mixed, [hap, hap[10:310]]))
+    spoiled = _uniform_indel_region(rng, 150, 17, hap)
+    b0, q0, i0, d0, c0 = spoiled[5]
+    spoiled[5] = (b0, q0, i0[:70] + bytes([30]) + i0[71:], d0, c0)
+    regs.append(Region(spoiled, [hap, hap[5:250]]))
+    b = FlatBatch.from_regions(regs)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+
+
+def test_all_uniform_form_underflow_fallback(hmm, oracle):
+    """All-uniform reads that underflow FP32 are queued for the FP64 kernels like any other read."""
+    rng = np.random.default_rng(77)
+    hap = bytes(rng.choice(list(b"ACGT"), 300).astype(np.uint8))
+    other = bytes(rng.choice(list(b"ACGT"), 300).astype(np.uint8))  # unrelated haplotype: tiny likelihoods
+    reads = _uniform_indel_region(rng, 250, 16, hap, 45, 45, 40)
+    b = FlatBatch.from_regions([Region(reads, [hap, other, other[::-1]])])
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    assert used.any() and not used.all()
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+
+
 def test_golden_fixtures(hmm):
     """Committed fixtures (tools/make_golden.py, oracle-scored): bit-exact raw FP32 sums and fallback
     flags, FP64 reruns to 1e-9, everything within the 1e-4 contract of the double-precision value."""

@@ -12,6 +12,9 @@
 // Packing chunk k+1 overlaps the GPU work of chunk k.
 #include "phmm_engine.h"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -69,18 +72,27 @@ static inline const ClassRef* f32_class_of_len(int form, int len) { return (len 
 static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid_by_len[len] : -1; }
 
 // The value all qualities of one plane of a read share (masked & 127 like the kernels), or -1.
+// Runs over every read of every call (up to three planes): 16 bytes per step, early exit.
 static int uniform_gcp(const uint8_t* c, int32_t len) {
   const uint8_t v = c[0] & 127u;
-  const uint64_t vv = 0x0101010101010101ull * v, m7 = 0x7f7f7f7f7f7f7f7full;
-  uint64_t diff = 0;
   int32_t i = 0;
-  for (; i + 8 <= len; i += 8) {  // eight quals per step (this scan runs over every read of every call)
+#if defined(__SSE2__)
+  const __m128i vv = _mm_set1_epi8((char)v), m7 = _mm_set1_epi8(0x7f);
+  for (; i + 16 <= len; i += 16) {
+    const __m128i w = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(c + i)), m7);
+    if (_mm_movemask_epi8(_mm_cmpeq_epi8(w, vv)) != 0xffff) return -1;
+  }
+#else
+  const uint64_t v8 = 0x0101010101010101ull * v, mask7 = 0x7f7f7f7f7f7f7f7full;
+  for (; i + 8 <= len; i += 8) {
     uint64_t w;
     std::memcpy(&w, c + i, 8);
-    diff |= (w & m7) ^ vv;
+    if ((w & mask7) != v8) return -1;
   }
-  for (; i < len; ++i) diff |= (uint64_t)((c[i] & 127u) ^ v);
-  return diff ? -1 : (int)v;
+#endif
+  for (; i < len; ++i)
+    if ((c[i] & 127u) != v) return -1;
+  return (int)v;
 }
 
 static cudaError_t init_slot(Slot& s);
@@ -276,6 +288,7 @@ struct Planner {
   int64_t max_cells;
   uint32_t hs_cols;  // haplotype columns per task (bounds the shared-memory stream)
   int sm_count = 148;
+  bool shape_tail = true;  // false for every chunk of a call but the last one on its device: their tails overlap the next chunk
 
   int run(const std::vector<int64_t>& regions, size_t first, size_t& next) {
     ChunkPlan& P = s.plan;
@@ -307,6 +320,53 @@ struct Planner {
       static const int force_min_g = (int)env_i64("FCS_PHMM_FORCE_MIN_G", -1);  // developer knob
       if (force_min_g >= 0) min_G = force_min_g;
     }
+    // Tail shaping works on the pairs that are still to come after a region (suffix sums over this
+    // chunk's regions): tasks are launched longest first, so what is cut finer here ends up in the last
+    // wave of CTAs.  One "wave" is about sm_count x 64 pairs (8 CTAs x 8 reads x 1 haplotype).
+    std::vector<uint64_t> pairs_after(regions.size() + 1, 0);
+    std::vector<size_t> qual_off(regions.size() + 1, 0);  // first read of each region in all_gcp / all_ukey
+    for (size_t kk = regions.size(); kk-- > first;) {
+      int32_t nr = 0, nh = 0;
+      in.shape(regions[kk], nr, nh);
+      pairs_after[kk] = pairs_after[kk + 1] + (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
+    }
+    // Which reads have constant qualities: gap continuation only (uniform-GCP form) or insertion and
+    // deletion as well (all-uniform form).  The all-uniform kernels are used only if they carry the bulk
+    // of the chunk: a thin extra launch spread over many (G, R) classes next to the main one costs more
+    // (instruction cache, 8-CTA/SM footprint) than its faster loop gains (measured on config 3: -7 %).
+    std::vector<int> all_gcp, all_ukey;
+    bool ua_chunk = false;
+    {
+      uint64_t n_elig = 0, n_tot = 0;
+      for (size_t kk = first; kk < regions.size(); ++kk) {
+        int32_t nr = 0, nh = 0;
+        in.shape(regions[kk], nr, nh);
+        qual_off[kk] = all_gcp.size();
+        if (nr <= 0 || nh <= 0) continue;
+        for (int32_t i = 0; i < nr; ++i) {
+          const InRead r = in.read(regions[kk], i);
+          int gq = -1, uk = -1;
+          if (r.len > 0 && r.i && r.d && r.c) {
+            gq = uniform_gcp(r.c, r.len);
+            if (gq >= 0) {
+              const int ui = uniform_gcp(r.i, r.len);
+              const int ud = ui >= 0 ? uniform_gcp(r.d, r.len) : -1;
+              if (ud >= 0) uk = gq | (ui << 8) | (ud << 16);
+            }
+          }
+          all_gcp.push_back(gq);
+          all_ukey.push_back(uk);
+          n_elig += uk >= 0;
+        }
+        n_tot += (uint64_t)nr;
+      }
+      static const bool ua_enabled = env_i64("FCS_PHMM_NO_UA", 0) == 0;  // developer knob: disable the all-uniform kernels
+      ua_chunk = ua_enabled && n_elig * 2 >= n_tot && n_tot > 0;
+    }
+    static const double tail1_x = (double)env_i64("FCS_PHMM_TAIL1_X100", 150) / 100.0;  // in waves: half-length tasks
+    static const double tail2_x = (double)env_i64("FCS_PHMM_TAIL2_X100", 50) / 100.0;   // in waves: wide lane groups, one haplotype
+    static const int tail2_g = (int)env_i64("FCS_PHMM_TAIL2_G", 16);
+    const uint64_t wave_pairs = (uint64_t)sm_count * 64u;
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps, ukeys;
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
@@ -337,14 +397,8 @@ struct Planner {
           return set_error(FCS_PHMM_EINVAL, "read with non-positive length or null array");
         if (r.len > FCS_PHMM_MAX_READ_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "read longer than FCS_PHMM_MAX_READ_LEN");
         lens[i] = (uint32_t)r.len;
-        gcps[i] = uniform_gcp(r.c, r.len);
-        // all-uniform key: continuation, insertion and deletion qualities constant over the read
-        ukeys[i] = -1;
-        if (gcps[i] >= 0) {
-          const int ui = uniform_gcp(r.i, r.len);
-          const int ud = ui >= 0 ? uniform_gcp(r.d, r.len) : -1;
-          if (ud >= 0) ukeys[i] = gcps[i] | (ui << 8) | (ud << 16);
-        }
+        gcps[i] = all_gcp[qual_off[k] + (size_t)i];
+        ukeys[i] = all_ukey[qual_off[k] + (size_t)i];
         sum_r += (uint64_t)r.len;
         rb += 5u * round_up16((uint32_t)r.len);
       }
@@ -373,19 +427,20 @@ struct Planner {
       for (int32_t i = 1; i < nr && same; ++i) same = lens[i] == lens[0];
       if (!same) std::stable_sort(ord, ord + nr, [&](uint32_t a, uint32_t b) { return lens[a] > lens[b]; });
       // ---- tasks
-      // Tail shaping: the last quarter of a chunk's regions is cut into tasks of half the haplotype
-      // columns.  Tasks are launched longest first, so the short ones fill the end of the grid and
-      // the last wave of CTAs is half as long (equal-size tasks finish in lock step otherwise).
-      static const int tail_pct = (int)env_i64("FCS_PHMM_TAIL_PCT", 25);
-      static const bool use_ua = env_i64("FCS_PHMM_NO_UA", 0) == 0;  // developer knob: disable the all-uniform kernels
-      const uint32_t cols_limit =
-          min_G ? 1u : ((k - first) * 100 >= (regions.size() - first) * (size_t)(100 - tail_pct) ? std::max(hs_cols / 2, 1u) : hs_cols);
+      // Tail shaping (equal-size tasks finish in lock step otherwise): the reads within the last ~1.5
+      // waves of the chunk are cut into tasks of half the haplotype columns, those within the last ~0.5
+      // wave into one-haplotype tasks on wide lane groups (a quarter of the run time of a regular task).
+      const bool use_ua = ua_chunk;
       const uint32_t read_base = (uint32_t)P.n_reads, hap_base = (uint32_t)P.n_haps;
       uint32_t maxlh = 0;
       for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
       const bool long_hap = maxlh >= (uint32_t)kGenericMinHapLen;
       s.gen_flags.resize(read_base + (size_t)nr, 0);
       for (int32_t i = 0; i < nr;) {
+        const double pairs_left = (double)(pairs_after[k + 1] + (uint64_t)(nr - i) * (uint64_t)nh);
+        const bool tail1 = shape_tail && pairs_left <= tail1_x * (double)wave_pairs;
+        const int wide_G = min_G ? min_G : ((shape_tail && pairs_left <= tail2_x * (double)wave_pairs) ? tail2_g : 0);
+        const uint32_t cols_limit = wide_G ? 1u : (tail1 ? std::max(hs_cols / 2, 1u) : hs_cols);
         if (long_hap || lens[ord[i]] > (uint32_t)kGenericMaxSinglePassRead) {
           // striped generic path: one (read, hap) pair per list entry
           s.gen_flags[read_base + (size_t)i] = 1;
@@ -398,12 +453,12 @@ struct Planner {
         // full groups of the longest remaining read use the table; the last, partly filled group of a
         // region asks for the class that is cheapest per read actually served
         const ClassRef* k0 = f32_class_of_len(false, (int)lens[ord[i]]);
-        if (min_G) k0 = select_class_wide(false, false, (int)lens[ord[i]], min_G);
+        if (wide_G) k0 = select_class_wide(false, false, (int)lens[ord[i]], wide_G);
         else if (nr - i < 32 / k0->G) k0 = select_class_for(false, false, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
         // All-uniform form: a full warp of reads that share one (continuation, insertion, deletion)
         // quality triple.  Throughput policy only; leftover groups and latency-bound calls keep the
         // wide-group classes of the other forms.
-        const ClassRef* ku = (!min_G && use_ua && ukeys[ord[i]] >= 0) ? f32_class_of_len(2, (int)lens[ord[i]]) : nullptr;
+        const ClassRef* ku = (!wide_G && use_ua && ukeys[ord[i]] >= 0) ? f32_class_of_len(2, (int)lens[ord[i]]) : nullptr;
         if (ku) {
           const int ngu = 32 / ku->G;
           if (nr - i < ngu) ku = nullptr;
@@ -1199,7 +1254,7 @@ int Engine::compute_one(const Input& in) {
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
       const double t0 = now_ms();
       size_t next = 0;
-      Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count};
+      Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count, c + 1 == dw.chunks.size()};
       rc = pl.run(dw.chunks[c], 0, next);
       if (rc == FCS_PHMM_OK && next != dw.chunks[c].size()) rc = set_error(FCS_PHMM_EUNSUPPORTED, "a single region exceeds the chunk limits (2^31 pairs / 2 GiB)");
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }

@@ -105,13 +105,21 @@ const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, 
 const ClassRef* select_class_wide(bool f64, int form, int read_len, int min_G) {
   std::call_once(g_once, build);
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
+  // memo per (form, length, min_G in {<=4, 8, 16, 32}); benign races (every thread computes the same pointer)
+  static std::atomic<const ClassRef*> memo[2 * kForms][kMaxSelLen + 1][4];
+  const int gb = min_G <= 4 ? 0 : (min_G <= 8 ? 1 : (min_G <= 16 ? 2 : 3));
+  std::atomic<const ClassRef*>& slot = memo[fidx(f64, form)][read_len][gb];
+  if (const ClassRef* hit = slot.load(std::memory_order_relaxed)) return hit;
+  min_G = gb == 0 ? min_G : (4 << gb);
   const ClassRef* best = nullptr;
   for (const ClassRef& k : g_classes[fidx(f64, form)]) {
     if (k.G * k.R < read_len + 1 || k.G < min_G) continue;
     // fewest rows per lane first (shortest dependent chain per step), then fewest lanes
     if (!best || k.R < best->R || (k.R == best->R && k.G < best->G)) best = &k;
   }
-  return best ? best : select_class(f64, form, read_len);
+  if (!best) best = select_class(f64, form, read_len);
+  slot.store(best, std::memory_order_relaxed);  // (every class has G >= 4, so all min_G <= 4 are equivalent)
+  return best;
 }
 
 const ClassRef* find_class(bool f64, int form, int G, int R) {

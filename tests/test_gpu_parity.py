@@ -175,6 +175,10 @@ def test_all_uniform_form_every_tile(hmm, oracle):
     spoiled = _uniform_indel_region(rng, 150, 17, hap)
     b0, q0, i0, d0, c0 = spoiled[5]
     spoiled[5] = (b0, q0, i0[:70] + bytes([30]) + i0[71:], d0, c0)
+    b1, q1, i1, d1, c1 = spoiled[11]
+    spoiled[11] = (b1, q1, i1, d1[:-1] + bytes([31]), c1)  # differs in the very last byte only
+    b2, q2, i2, d2, c2 = spoiled[2]
+    spoiled[2] = (b2, q2, i2, d2, c2[:147] + bytes([11]) + c2[148:])
     regs.append(Region(spoiled, [hap, hap[5:250]]))
     b = FlatBatch.from_regions(regs)
     out, used, raw = hmm.compute_flat(b, want_raw=True)

@@ -121,8 +121,10 @@ def test_batcher_covers_every_pair_exactly_once():
     info = plan_check(b)
     assert info["n_pairs"] == b.n_pairs and info["n_generic_pairs"] > 0 and info["n_tasks"] > 0
     assert info["max_smem_bytes"] <= 227 * 1024 and info["n_sym"] == 6
-    for mk, lo in ((synth.config2_uniform, 0.95), (synth.config1_golden, 0.90)):
-        bb = mk(n_regions=40)
+    # (tail shaping trades geometric efficiency for a short last wave on the final ~24k pairs, so measure
+    # the efficiency on batches well above that)
+    for mk, n_regions, lo in ((synth.config2_uniform, 100, 0.95), (synth.config1_golden, 400, 0.90)):
+        bb = mk(n_regions=n_regions)
         i2 = plan_check(bb)
         assert i2["n_pairs"] == bb.n_pairs and i2["n_generic_pairs"] == 0 and i2["geometric_efficiency"] >= lo and i2["n_sym"] == 5
     tiny = plan_check(synth.tiny_mixed(seed=2, n_regions=2))

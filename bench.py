@@ -33,7 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu capture
-NCU_DRAM_BYTES_PER_LAUNCH = {"c2": 8845312}
+NCU_DRAM_BYTES_PER_LAUNCH = {"c2": 4496896}
 
 METRIC = "pairhmm_gcups"
 UNIT = "GCUPS"
@@ -321,10 +321,11 @@ def main():
                     "call": "fcs_pairhmm_compute(handle, regions, n_regions): pack from caller pointers -> pinned staging -> H2D -> kernels -> D2H -> scatter"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "fp32_fma", "achieved": main_gcups, "peak": peak_gcups, "unit": UNIT, "frac": main_gcups / peak_gcups,
-                         "frac_at_sustained_clock": main_gcups / (n_sm * 128 * f_sus / 8.0), "kernel": "phmm_f32u_tier1 / phmm_f32*_tier* (FP32 wavefront, run_task<float,G,R,UG>)",
+                         "frac_at_sustained_clock": main_gcups / (n_sm * 128 * f_sus / 8.0), "kernel": "phmm_f32a_tier2 on config 2 (all-uniform form, G=4 R=38) / phmm_f32*_tier* (FP32 wavefront, run_task<float,G,R,FORM>)",
                          "per_unit": "8 FMA-pipe instructions (4 FFMA + 4 FMUL, 12 FLOP) per DP cell", "n_sm": n_sm, "f_max_ghz": f_max,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "traffic_note": "dram__bytes_read+write of one FP32-kernel launch, "
-                         "ncu --set full capture profiles/r01_c2_fp32u_tier1_full.md (config 2 only; equals the algorithmic input bytes, no re-reads)",
+                         "ncu --set full capture profiles/r01_c2_fp32a_tier2_full.md (config 2 only; the all-uniform kernel reads bases + base quals + haplotypes once, "
+                         "the leftover launch the rest: no re-reads)",
                          "algorithmic_bytes": alg_bytes, "hbm": {"achieved_gbs": alg_bytes * args.steps / (t_max * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                                                   "peak_source": peaks_src, "note": "HBM is non-binding for this path"}},
             "clocks": clocks, "wall_s_timed_region": wall,

@@ -844,16 +844,18 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   CK(cudaEventRecord(s.ev_k0, s.stream));
   // Fork: launch i goes to stream i % (1 + kSide); the side streams start after the upload and are
   // joined before the next phase, so launches of different classes fill each other's tails.
+  // (only the side streams that get a launch are forked and joined: every call here is a driver round
+  // trip on the host's critical path, and a small chunk has ~30 of them)
   auto fork = [&](int n_launches) -> cudaError_t {
     if (n_launches <= 1) return cudaSuccess;
     cudaError_t e = cudaEventRecord(s.ev_fork, s.stream);
-    for (int i = 0; i < Slot::kSide && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s.side[i], s.ev_fork, 0);
+    for (int i = 0; i < std::min(Slot::kSide, n_launches - 1) && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s.side[i], s.ev_fork, 0);
     return e;
   };
   auto join = [&](int n_launches) -> cudaError_t {
     if (n_launches <= 1) return cudaSuccess;
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < Slot::kSide && e == cudaSuccess; ++i) {
+    for (int i = 0; i < std::min(Slot::kSide, n_launches - 1) && e == cudaSuccess; ++i) {
       e = cudaEventRecord(s.ev_side[i], s.side[i]);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(s.stream, s.ev_side[i], 0);
     }
@@ -1207,7 +1209,8 @@ int Engine::compute_one(const Input& in) {
     int64_t limit = max_chunk_cells_;
     const bool ramp = limit <= 0;
     if (limit <= 0) {
-      const int64_t want = (int64_t)(total / (uint64_t)(2 * std::max(1, pack_threads_)));
+      static const int64_t cpt_x10 = env_i64("FCS_PHMM_CHUNKS_PER_THREAD_X10", 20);  // developer knob
+      const int64_t want = (int64_t)(total * 10 / (uint64_t)(cpt_x10 * std::max(1, pack_threads_)));
       limit = std::min<int64_t>(8000000000LL, std::max<int64_t>(500000000LL, want));
     }
     uint64_t cells = 0, pairs = 0, bytes = 0;

@@ -351,7 +351,8 @@ struct Planner {
             if (gq >= 0) {
               const int ui = uniform_gcp(r.i, r.len);
               const int ud = ui >= 0 ? uniform_gcp(r.d, r.len) : -1;
-              if (ud >= 0) uk = gq | (ui << 8) | (ud << 16);
+              // (equal insertion and deletion quality, as GATK writes them: the kernels share M * pMX = M * pMY)
+              if (ud >= 0 && ud == ui) uk = gq | (ui << 8) | (ud << 16);
             }
           }
           all_gcp.push_back(gq);
@@ -812,7 +813,7 @@ void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) 
   p.hap_stage_bytes = 0;
   p.n_sym = P.n_sym;
   p.c_xx_f = 0.f; p.c_gm_f = 0.f; p.c_xx_d = 0.0; p.c_gm_d = 0.0;
-  p.c_mm_f = 0.f; p.c_mx_f = 0.f; p.c_my_f = 0.f;
+  p.c_mm_f = 0.f; p.c_mx_f = 0.f;
 }
 
 // launch constants of a uniform-GCP / all-uniform launch, from the same tables the kernels index.
@@ -824,8 +825,7 @@ static void set_gcp_constants(KParams& p, int key) {
   const uint32_t iq = (uint32_t)(key >> 8) & 127u, dq = (uint32_t)(key >> 16) & 127u;
   const uint32_t mn = std::min(iq, dq), mx = std::max(iq, dq);
   p.c_mm_f = L.mm_f[((mx * (mx + 1u)) >> 1) + mn];
-  p.c_mx_f = L.ph2pr_f[iq];
-  p.c_my_f = L.ph2pr_f[dq];
+  p.c_mx_f = L.ph2pr_f[iq];  // == ph2pr[dq]: the all-uniform key requires iq == dq
   p.c_xx_f = L.ph2pr_f[gcp & 127];
   p.c_gm_f = 1.0f - p.c_xx_f;
   p.c_xx_d = L.ph2pr_d[gcp & 127];

@@ -155,11 +155,14 @@ struct Layout {
 // form, 17 with UG (and 7 instead of 8 registers per row).  Only the Y update keeps a per-row
 // multiplier (pYY[k] = 1 on the rows above the read, so their Y stays K/Lh).
 //
-// FORM 2, UA ("uniform all"): the insertion and deletion qualities are constant over the reads of
+// FORM 2, UA ("uniform all"): the insertion and deletion qualities are one constant over the reads of
 // the launch as well (GATK without the PCR indel model, i.e. PCR-free libraries: 45/45; BASELINE
-// config 2).  Then pMM, pMX and pMY are launch constants too: 14 register operands per cell and 4
-// registers per row (M, X, Y, pYY), which lets a lane hold up to 38 rows -- a 150-bp read on FOUR
-// lanes, eight reads per warp, half the wavefront skew.  The rows above the read need no per-row
+// config 2; GATK always writes equal insertion and deletion qualities).  Then pMM and pMX = pMY are
+// launch constants too, and the product M[r][c] * pMX is needed twice -- by X[r+1][c] in this step
+// and by Y[r][c+1] in the next one -- so it is computed once and kept (State::P): SEVEN FMA-pipe
+// instructions per cell instead of eight, 13 register operands, 5 registers per row (M, X, Y, P,
+// pYY), which lets a lane hold up to 38 rows -- a 150-bp read on FOUR lanes, eight reads per warp,
+// half the wavefront skew.  Same values in the same operations as the other forms => same bits.  The rows above the read need no per-row
 // zeros here: their prior is 0, so M = 0; X of tile row 0 is forced to 0 by its own register pair
 // (pXX[0], pMX[0]) and every X below it is fma(0, cXX, 0 * cMX) = 0; Y keeps pYY[k] = 1.
 template <typename T, int G, int R, int FORM>
@@ -179,7 +182,7 @@ struct Tile {
   T pGM[RG], pXX[RG];  // general form: per row.  UG: [0] only (pXX[0] = X multiplier of tile row 0)
   T pYY[UG ? R : 1];   // UG: per-row Y multiplier.  general: [0] = Y multiplier of tile row 0
   T cXX, cGM;          // UG: launch constants
-  T cMM, cMX, cMY;     // UA: launch constants
+  T cMM, cMX;          // UA: launch constants (pMY == pMX: insertion and deletion quality are equal)
   int npl;             // rows of this lane that lie above the read (always its first rows)
   int off_last;        // ROT: byte offset of this lane's last 16-byte chunk from its (rotated) row base
 
@@ -192,7 +195,7 @@ struct Tile {
   __device__ __forceinline__ T yy(int k) const { return UG ? pYY[UG ? k : 0] : (k == 0 ? pYY[0] : pXX[UG ? 0 : k]); }
   __device__ __forceinline__ T mm_(int k) const { return UA ? cMM : pMM[UA ? 0 : k]; }
   __device__ __forceinline__ T mx(int k) const { return UA ? (k == 0 ? pMX[0] : cMX) : pMX[UA ? 0 : k]; }
-  __device__ __forceinline__ T my(int k) const { return UA ? cMY : pMY[UA ? 0 : k]; }
+  __device__ __forceinline__ T my(int k) const { return UA ? cMX : pMY[UA ? 0 : k]; }
 
   // Fill constants and this lane's slice of the prior table from the staged read.
   // tab_lane = table base + lane_base(lane).  rs points at the group's read blob (planes of Lp bytes; staged in shared memory, or in global
@@ -265,6 +268,7 @@ struct Tile {
   // from the lane above one step ago (= the diagonal inputs of tile row 0) and the running sum.
   struct State {
     T M[R], X[R], Y[R];
+    T P[UA ? R : 1];  // UA: M[k] * cMX of the same column (made for X of the row below, reused for Y of the next column)
     T dM, dX, dY;
     T acc;
   };
@@ -275,6 +279,7 @@ struct Tile {
       st.M[k] = T(0);
       st.X[k] = T(0);
       st.Y[k] = (k < npl) ? y_init : T(0);
+      if constexpr (UA) st.P[k] = T(0);
     }
     st.dM = T(0);
     st.dX = T(0);
@@ -306,11 +311,19 @@ struct Tile {
       s = A::fma(xd, gm(k), s);
       s = A::fma(yd, gm(k), s);
       nM[k] = A::mul(s, pr[k]);
-      nY[k] = A::fma(st.Y[k], yy(k), A::mul(st.M[k], my(k)));
+      if constexpr (UA) nY[k] = A::fma(st.Y[k], yy(k), st.P[k]);
+      else nY[k] = A::fma(st.Y[k], yy(k), A::mul(st.M[k], my(k)));
     }
     nX[0] = A::fma(uX, xx(0), A::mul(uM, mx(0)));
+    if constexpr (UA) {
 #pragma unroll
-    for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), A::mul(nM[k - 1], mx(k)));
+      for (int k = 0; k < R; ++k) st.P[k] = A::mul(nM[k], cMX);
+#pragma unroll
+      for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), st.P[k - 1]);
+    } else {
+#pragma unroll
+      for (int k = 1; k < R; ++k) nX[k] = A::fma(nX[k - 1], xx(k), A::mul(nM[k - 1], mx(k)));
+    }
     st.acc = A::add(st.acc, A::add(nM[R - 1], nX[R - 1]));
     st.dM = uM; st.dX = uX; st.dY = uY;
 #pragma unroll
@@ -384,8 +397,8 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
   Tile<T, G, R, FORM> tile;
-  if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; tile.cMM = p.c_mm_f; tile.cMX = p.c_mx_f; tile.cMY = p.c_my_f; }
-  else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; tile.cMM = T(0); tile.cMX = T(0); tile.cMY = T(0); }
+  if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; tile.cMM = p.c_mm_f; tile.cMX = p.c_mx_f; }
+  else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; tile.cMM = T(0); tile.cMX = T(0); }
 
   const bool active = grp < (int)task.n_reads;
   const uint32_t read = task.read0 + (active ? grp : 0);
@@ -463,7 +476,7 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
   Tile<T, G, R, FORM> tile;
   if constexpr (sizeof(T) == 4) { tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; }
   else { tile.cXX = p.c_xx_d; tile.cGM = p.c_gm_d; }
-  tile.cMM = T(0); tile.cMX = T(0); tile.cMY = T(0);
+  tile.cMM = T(0); tile.cMX = T(0);
   const RerunEntry* list = p.rerun + p.rerun_base[qid];
   for (uint32_t base = cta * NG; base < count; base += nctas * NG) {
     const bool active = base + grp < count;

@@ -90,8 +90,8 @@ struct KParams {
   // uniform-GCP launches: ph2pr[gcp] and 1 - ph2pr[gcp], read from the constant bank
   float c_xx_f, c_gm_f;
   double c_xx_d, c_gm_d;
-  // all-uniform launches (FP32 only): matchToMatch[ins, del], ph2pr[ins], ph2pr[del]
-  float c_mm_f, c_mx_f, c_my_f;
+  // all-uniform launches (FP32 only; insertion quality == deletion quality): matchToMatch[q, q], ph2pr[q]
+  float c_mm_f, c_mx_f;
 };
 
 PHMM_HD inline constexpr uint32_t round_up16(uint32_t x) { return (x + 15u) & ~15u; }

@@ -165,7 +165,7 @@ def test_all_uniform_form_every_tile(hmm, oracle):
             150, 151, 152, 159, 160, 167, 168, 175, 183, 184, 199, 200, 215, 216, 231, 239, 240, 250, 255, 256, 271, 287, 288,
             295, 296, 302, 303, 304, 320]
     for n, L in enumerate(lens):
-        trip = [(45, 45, 10), (40, 30, 10), (45, 45, 12), (20, 45, 3)][n % 4]
+        trip = [(45, 45, 10), (40, 40, 10), (30, 30, 12), (20, 45, 3)][n % 4]  # the last one (ins != del) must not take the UA kernels
         reads = _uniform_indel_region(rng, L, 8 if L < 152 else 4, hap, *trip, n_rate=0.01 if n % 5 == 0 else 0.0)
         haps = [hap, hap[:120], hap[33:]] + ([bytes(hap_n)] if n % 3 == 0 else [])
         regs.append(Region(reads, haps))

@@ -950,7 +950,8 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
         p.seg_max[k] = r.seg_max[k];
         p.seg_cta0[k] = grid;
         const unsigned ng = 32u / r.seg_G[k];
-        grid += std::min((r.seg_cap[k] + ng - 1) / ng, resident);
+        static const unsigned grid_cap = (unsigned)env_i64("FCS_PHMM_F64_GRID_CAP", 0);  // developer knob
+        grid += std::min(std::min((r.seg_cap[k] + ng - 1) / ng, resident), grid_cap ? grid_cap : ~0u);
       }
       p.seg_cta0[r.n_seg] = grid;
       CK(r.tk->launch(p, grid, r.smem, pick(li++, nl)));
@@ -1159,6 +1160,17 @@ int Engine::compute_one(const Input& in) {
   }
   const size_t D = devs_.size();
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
+  static const bool timeline = env_i64("FCS_PHMM_TIMELINE", 0) != 0;  // developer knob: host timeline of the call on stderr
+  const double tl0 = now_ms();
+  std::mutex tl_mu;
+  std::string tl_text;
+  auto tl_mark = [&](const char* what, int w, size_t c) {
+    if (!timeline) return;
+    char buf[96];
+    snprintf(buf, sizeof buf, " %s[w%d c%zu]@%.3f", what, w, c, now_ms() - tl0);
+    std::lock_guard<std::mutex> l(tl_mu);
+    tl_text += buf;
+  };
   // ---- size every region once
   std::vector<uint64_t> rc_cells((size_t)n), rc_pairs((size_t)n), rc_bytes((size_t)n);
   for (int64_t g = 0; g < n; ++g) {
@@ -1194,7 +1206,9 @@ int Engine::compute_one(const Input& in) {
   // ---- per device: chunk boundaries (cells, pairs and byte limits).  Unless the caller fixed a chunk
   // size, aim at about two chunks per packing thread: enough to pipeline host packing against the
   // device, few enough that each launch still has a device-filling number of tasks.  The first chunk
-  // of every packing thread is a quarter of the regular size so that the device starts early.
+  // of every packing thread is a quarter of the regular size so that the device starts early, the
+  // second a half: the host packs ~2.3x faster than the device computes, so sizes may double per round
+  // without the device running dry (a 4x jump left it idle: config 2 x8 e2e 3343 -> 3646 GCUPS).
   struct DevWork {
     std::vector<std::vector<int64_t>> chunks;
     std::atomic<size_t> next{0};
@@ -1218,7 +1232,10 @@ int Engine::compute_one(const Input& in) {
     auto& chunks = work[d].chunks;
     for (int64_t g : part[d]) {
       const size_t k = (size_t)g;
-      const int64_t lim_now = (ramp && (int)chunks.size() < pack_threads_) ? std::max<int64_t>(limit / 4, 125000000LL) : limit;
+      static const int ramp_style = (int)env_i64("FCS_PHMM_RAMP", 1);
+      int64_t lim_now = limit;
+      if (ramp && (int)chunks.size() < pack_threads_) lim_now = std::max<int64_t>(limit / 4, 125000000LL);
+      else if (ramp && ramp_style == 1 && (int)chunks.size() < 2 * pack_threads_) lim_now = std::max<int64_t>(limit / 2, 125000000LL);
       if (!cur.empty() && cells > 0 &&
           ((int64_t)(cells + rc_cells[k]) > lim_now || pairs + rc_pairs[k] > 0x7fffffffULL || bytes + rc_bytes[k] > (1ull << 31))) {
         chunks.emplace_back(std::move(cur));
@@ -1233,6 +1250,7 @@ int Engine::compute_one(const Input& in) {
     for (int w = 0; w < work[d].threads; ++w) jobs.emplace_back((int)d, w);
     n_jobs += work[d].threads;
   }
+  tl_mark("sized+chunked", -1, 0);
   std::atomic<int> first_rc{FCS_PHMM_OK};
   std::mutex err_mu;
   std::string err_text;
@@ -1253,8 +1271,10 @@ int Engine::compute_one(const Input& in) {
       const size_t c = dw.next.fetch_add(1);
       if (c >= dw.chunks.size()) break;
       Slot& s = d.slots[(size_t)2 * w + (size_t)(use++ & 1)];
+      tl_mark("take", w, c);
       int rc = retire_slot(d, s);
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
+      tl_mark("retired", w, c);
       const double t0 = now_ms();
       size_t next = 0;
       Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count, c + 1 == dw.chunks.size()};
@@ -1265,6 +1285,7 @@ int Engine::compute_one(const Input& in) {
       rc = ensure_buffers(s, s.plan.in_bytes, s.plan.total_bytes - s.plan.off_out, s.plan.total_bytes);
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
       const double t1 = now_ms();
+      tl_mark("planned", w, c);
       rc = pack_chunk(s, in);
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
       {
@@ -1273,17 +1294,21 @@ int Engine::compute_one(const Input& in) {
         stats_.pack_ms += now_ms() - t1;
       }
       s.input = &in;
+      tl_mark("packed", w, c);
       rc = launch_chunk(d, s, true, true);
       if (rc != FCS_PHMM_OK) { cudaStreamSynchronize(s.stream); fail_with(rc); break; }
       s.busy = true;
+      tl_mark("launched", w, c);
     }
     for (int k = 0; k < 2; ++k) {
       int r2 = retire_slot(d, d.slots[(size_t)2 * w + k]);
       if (r2 != FCS_PHMM_OK) fail_with(r2);
+      tl_mark("drained", w, (size_t)k);
     }
   };
   if (n_jobs == 1) worker(0);
   else pool_->run(n_jobs, worker);
+  if (timeline) fprintf(stderr, "[fcs_phmm timeline, ms]%s end@%.3f\n", tl_text.c_str(), now_ms() - tl0);
   if (first_rc.load() != FCS_PHMM_OK) return set_error(first_rc.load(), err_text);
   return FCS_PHMM_OK;
 }

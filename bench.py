@@ -123,11 +123,20 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def host_threads() -> int:
+    """All host cores this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    to its ranks, which would make the CPU reference arm single-threaded at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(batch, reps: int = 3, nthreads: int = 0):
     from oracle import oracle as O
 
     O.load()
-    nthreads = nthreads or O.max_threads()
+    nthreads = nthreads or host_threads()
     O.batch_simd(batch.select(range(min(4, batch.n_regions))), nthreads, True)  # warm the thread pool / tables
     ts = []
     nd = 0
@@ -156,7 +165,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
 
     O.load()
-    nthreads = O.max_threads()
+    nthreads = host_threads()
     for _ in range(max(1, min(args.warmup, 2))):
         O.batch_simd(batch, nthreads, True)
     ts = []

@@ -43,6 +43,9 @@
 
 namespace fcsphmm {
 
+#ifndef PHMM_UNROLL2_ABOVE
+#define PHMM_UNROLL2_ABOVE 24
+#endif
 constexpr int kUnrollT = PHMM_UNROLL_T;  // steps per loop trip (even, so the state arrays rotate without MOVs; 4 measured best: +4 % over 2)
 
 // ----------------------------------------------------------------------------------------
@@ -174,7 +177,7 @@ struct Tile {
   static constexpr int NV = (R * (int)sizeof(T) + 15) / 16;
   static constexpr int VW = 16 / (int)sizeof(T);
   // steps per loop trip: the unrolled body should stay near 650 instructions (instruction cache)
-  static constexpr int UNROLL = (R > 24) ? 2 : kUnrollT;
+  static constexpr int UNROLL = (R > PHMM_UNROLL2_ABOVE) ? 2 : kUnrollT;
   static constexpr int RG = UG ? 1 : R;  // rows that keep their own pGM / pXX
   static constexpr int RA = UA ? 1 : R;  // rows that keep their own pMM / pMX / pMY
 

@@ -7,7 +7,7 @@
 One "step" = one pass of the PairHMM forward path over one synthetic batch of the workload
 (default: BASELINE config 2 — 100 000 pairs, 150 bp reads x 300 bp haplotypes, uniform quals).
   value      GCUPS, kernels only, inputs already resident in HBM (CUDA events on the library's
-             launching stream, L2 flushed between steps, max over ranks)
+             launching stream, steps rotate over resident batches totalling more than L2 (or --l2 flush), max over ranks)
   e2e        same metric through the reference-facing call fcs_pairhmm_compute() with HOST buffers:
              host packing + H2D + kernels + D2H + scatter inside the timed region
   roofline   FP32 FMA pipe: peak GCUPS = n_SM * 128 * f_max / 8

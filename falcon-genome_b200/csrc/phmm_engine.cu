@@ -1509,7 +1509,11 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
   out->n_tasks = (int64_t)P.n_tasks;
   out->n_generic_pairs = (int64_t)P.n_gen;
   out->n_launches_f32 = 0;
-  for (const auto& r : P.f32) out->n_launches_f32 += r.n_tasks ? 1 : 0;
+  out->n_tasks_general = out->n_tasks_uniform_gcp = out->n_tasks_all_uniform = 0;
+  for (const auto& r : P.f32) {
+    out->n_launches_f32 += r.n_tasks ? 1 : 0;
+    (r.tk->form == 2 ? out->n_tasks_all_uniform : (r.tk->form == 1 ? out->n_tasks_uniform_gcp : out->n_tasks_general)) += (int64_t)r.n_tasks;
+  }
   out->n_launches_f32 += P.n_gen ? 1 : 0;
   out->n_launches_f64 = (int32_t)P.f64.size() + (P.gen64_cap ? 1 : 0);
   out->n_sym = (int32_t)P.n_sym;

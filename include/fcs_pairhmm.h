@@ -236,6 +236,8 @@ typedef struct {
   int32_t n_launches_f32, n_launches_f64, n_sym, latency_mode;
   double geometric_efficiency; /* useful cells / cells swept by the tiles of the FP32 tasks */
   double plan_ms, pack_ms;
+  /* FP32 tasks per kernel form: general, uniform gap-continuation quality, all transition qualities uniform */
+  int64_t n_tasks_general, n_tasks_uniform_gcp, n_tasks_all_uniform;
 } fcs_phmm_plan_info;
 FCS_PHMM_API int fcs_pairhmm_plan_check(const fcs_phmm_flat_batch* b, int32_t sm_count, fcs_phmm_plan_info* out);
 /* The transition / prior lookup tables the kernels use, for bit-level checks against the oracle

@@ -129,3 +129,43 @@ def test_batcher_covers_every_pair_exactly_once():
         assert i2["n_pairs"] == bb.n_pairs and i2["n_generic_pairs"] == 0 and i2["geometric_efficiency"] >= lo and i2["n_sym"] == 5
     tiny = plan_check(synth.tiny_mixed(seed=2, n_regions=2))
     assert tiny["latency_mode"] == 1  # an under-filled call switches to the widest lane groups
+
+
+def test_planner_picks_the_kernel_form_from_the_qualities():
+    """Host-only (fcs_pairhmm_plan_check): constant insertion == deletion and continuation qualities -> all-uniform
+    kernels for the full warps of reads; anything else -> uniform-GCP or general form; a chunk in which the eligible
+    reads are a minority does not use the all-uniform kernels at all."""
+    from falcon_genome_b200 import plan_check
+
+    rng = np.random.default_rng(3)
+    hap = bytes(rng.choice(list(b"ACGT"), 300).astype(np.uint8))
+
+    def region(n_reads, L, ins, dele, gcp, spoil=None):
+        reads = []
+        for r in range(n_reads):
+            i = bytearray([ins] * L)
+            c = bytearray([gcp] * L)
+            if spoil == "ins" and r % 2 == 0:
+                i[L // 2] = ins - 5
+            if spoil == "gcp":
+                c[r % L] = gcp + 1
+            reads.append((hap[:L], bytes([30] * L), bytes(i), bytes([dele] * L), bytes(c)))
+        return Region(reads, [hap, hap[10:290], hap[5:280], hap[20:300]])
+
+    def forms(regs):
+        i = plan_check(FlatBatch.from_regions(regs))
+        assert i["n_tasks"] == i["n_tasks_general"] + i["n_tasks_uniform_gcp"] + i["n_tasks_all_uniform"]
+        return i["n_tasks_general"], i["n_tasks_uniform_gcp"], i["n_tasks_all_uniform"]
+
+    big = 400  # regions: well above the tail-shaping window, which uses wide uniform-GCP classes
+    g, u, a = forms([region(32, 150, 45, 45, 10) for _ in range(big)])
+    assert g == 0 and a >= big  # (u > 0 too: the last half wave of a batch runs on wide uniform-GCP classes)
+    g, u, a = forms([region(16, 150, 45, 40, 10) for _ in range(big)])  # ins != del: the shared product does not apply
+    assert g == 0 and a == 0 and u > 0
+    g, u, a = forms([region(16, 150, 45, 45, 10, spoil="gcp") for _ in range(big)])  # per-read GCP not constant
+    assert u == 0 and a == 0 and g > 0
+    g, u, a = forms([region(16, 150, 45, 45, 10, spoil="ins") for _ in range(big)])  # half of the reads eligible, interleaved
+    assert g == 0 and u > 0  # groups that mix eligible and non-eligible reads fall back
+    minority = [region(16, 150, 45, 45, 10) for _ in range(big // 4)] + [region(16, 150, 45, 40, 10) for _ in range(big)]
+    g, u, a = forms(minority)
+    assert a == 0 and u > 0

@@ -200,6 +200,14 @@ static cudaError_t init_slot(Slot& s) {
   if ((e = cudaEventCreate(&s.ev_k2)) != cudaSuccess) return e;
   if ((e = cudaEventCreate(&s.ev_done)) != cudaSuccess) return e;
   if ((e = cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+  {
+    int prio_lo = 0, prio_hi = 0;
+    if ((e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi)) != cudaSuccess) return e;
+    for (int i = 0; i < Slot::kHp; ++i) {
+      if ((e = cudaStreamCreateWithPriority(&s.hp[i], cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&s.ev_hp[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+  }
   for (int i = 0; i < Slot::kSide; ++i) {
     if ((e = cudaStreamCreateWithFlags(&s.side[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&s.ev_side[i], cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -209,6 +217,10 @@ static cudaError_t init_slot(Slot& s) {
 
 static void free_slot(Slot& s) {
   if (s.stream) cudaStreamSynchronize(s.stream);
+  for (int i = 0; i < Slot::kHp; ++i) {
+    if (s.hp[i]) { cudaStreamSynchronize(s.hp[i]); cudaStreamDestroy(s.hp[i]); }
+    if (s.ev_hp[i]) cudaEventDestroy(s.ev_hp[i]);
+  }
   for (int i = 0; i < Slot::kSide; ++i) {
     if (s.side[i]) { cudaStreamSynchronize(s.side[i]); cudaStreamDestroy(s.side[i]); }
     if (s.ev_side[i]) cudaEventDestroy(s.ev_side[i]);
@@ -925,11 +937,20 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   {
     const int nl = (int)P.f64.size() + (P.gen64_cap ? 1 : 0);
     int li = 0;
-    CK(fork(nl));
+    static const bool f64_prio = env_i64("FCS_PHMM_F64_PRIO", 1) != 0;  // developer knob
+    const bool hp = f64_prio && upload && nl > 0;  // (resident batches run alone: nothing to overtake)
+    const int n_hp = std::min(nl, (int)Slot::kHp);
+    auto pick64 = [&](int i) { return hp ? s.hp[i % Slot::kHp] : pick(i, nl); };
+    if (hp) {
+      CK(cudaEventRecord(s.ev_fork, s.stream));
+      for (int i = 0; i < n_hp; ++i) CK(cudaStreamWaitEvent(s.hp[i], s.ev_fork, 0));
+    } else {
+      CK(fork(nl));
+    }
     if (P.gen64_cap) {
       KParams p;
       fill_kparams(d, s, p, true);
-      CK(launch_generic_f64(p, std::min(P.gen_ctas, P.gen64_cap), pick(li++, nl)));
+      CK(launch_generic_f64(p, std::min(P.gen_ctas, P.gen64_cap), pick64(li++)));
       stats_.launches += 1;
     }
     for (const F64Range& r : P.f64) {
@@ -954,10 +975,17 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
         grid += std::min(std::min((r.seg_cap[k] + ng - 1) / ng, resident), grid_cap ? grid_cap : ~0u);
       }
       p.seg_cta0[r.n_seg] = grid;
-      CK(r.tk->launch(p, grid, r.smem, pick(li++, nl)));
+      CK(r.tk->launch(p, grid, r.smem, pick64(li++)));
       stats_.launches += 1;
     }
-    CK(join(nl));
+    if (hp) {
+      for (int i = 0; i < n_hp; ++i) {
+        CK(cudaEventRecord(s.ev_hp[i], s.hp[i]));
+        CK(cudaStreamWaitEvent(s.stream, s.ev_hp[i], 0));
+      }
+    } else {
+      CK(join(nl));
+    }
   }
   CK(cudaEventRecord(s.ev_k2, s.stream));
   if (download && P.n_pairs) {
@@ -970,6 +998,11 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
 }
 
 // Wait for the slot's chunk and scatter its results into the caller's arrays.
+// developer probe (FCS_PHMM_TIMELINE=1): device-side times of every chunk relative to the start of the call
+static cudaEvent_t g_tl_ref = nullptr;
+static std::mutex g_tl_mu;
+static std::string g_tl_gpu;
+
 int Engine::retire_slot(Device& d, Slot& s) {
   (void)d;
   if (!s.busy) return FCS_PHMM_OK;
@@ -981,6 +1014,17 @@ int Engine::retire_slot(Device& d, Slot& s) {
   float ms_all = 0.f, ms_main = 0.f;
   CK(cudaEventElapsedTime(&ms_all, s.ev_k0, s.ev_k2));
   CK(cudaEventElapsedTime(&ms_main, s.ev_k0, s.ev_k1));
+  if (g_tl_ref) {
+    float a = 0, b = 0, c = 0, e = 0;
+    cudaEventElapsedTime(&a, g_tl_ref, s.ev_k0);
+    cudaEventElapsedTime(&b, g_tl_ref, s.ev_k1);
+    cudaEventElapsedTime(&c, g_tl_ref, s.ev_k2);
+    cudaEventElapsedTime(&e, g_tl_ref, s.ev_done);
+    char buf[160];
+    snprintf(buf, sizeof buf, "\n  gpu chunk %5.2f Gcells: h2d done/kernels start %.3f  fp32 done %.3f  fp64 done %.3f  d2h done %.3f", s.plan.cells / 1e9, a, b, c, e);
+    std::lock_guard<std::mutex> l(g_tl_mu);
+    g_tl_gpu += buf;
+  }
   const double* out = reinterpret_cast<const double*>(s.h_out);
   const uint8_t* used = s.h_out + (P.off_used - P.off_out);
   const float* raw = reinterpret_cast<const float*>(s.h_out + (P.off_raw - P.off_out));
@@ -1162,6 +1206,13 @@ int Engine::compute_one(const Input& in) {
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
   static const bool timeline = env_i64("FCS_PHMM_TIMELINE", 0) != 0;  // developer knob: host timeline of the call on stderr
   const double tl0 = now_ms();
+  if (timeline && D == 1) {
+    if (!g_tl_ref) cudaEventCreate(&g_tl_ref);
+    cudaSetDevice(devs_[0]->ordinal);
+    cudaEventRecord(g_tl_ref, devs_[0]->slots[0].stream);
+    std::lock_guard<std::mutex> l(g_tl_mu);
+    g_tl_gpu.clear();
+  }
   std::mutex tl_mu;
   std::string tl_text;
   auto tl_mark = [&](const char* what, int w, size_t c) {
@@ -1308,7 +1359,7 @@ int Engine::compute_one(const Input& in) {
   };
   if (n_jobs == 1) worker(0);
   else pool_->run(n_jobs, worker);
-  if (timeline) fprintf(stderr, "[fcs_phmm timeline, ms]%s end@%.3f\n", tl_text.c_str(), now_ms() - tl0);
+  if (timeline) fprintf(stderr, "[fcs_phmm timeline, ms]%s end@%.3f%s\n", tl_text.c_str(), now_ms() - tl0, g_tl_gpu.c_str());
   if (first_rc.load() != FCS_PHMM_OK) return set_error(first_rc.load(), err_text);
   return FCS_PHMM_OK;
 }

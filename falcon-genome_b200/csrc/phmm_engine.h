@@ -102,6 +102,12 @@ struct Slot {
   cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_side[kSide] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
+  // the FP64 rerun launches go to high-priority streams: their CTAs (mostly empty: a handful of pairs per
+  // chunk) are then scheduled as soon as a slot frees up instead of queueing behind the FP32 CTAs of the
+  // chunks that were launched in the meantime, which would hold back this chunk's download
+  static constexpr int kHp = 2;
+  cudaStream_t hp[kHp] = {nullptr, nullptr};
+  cudaEvent_t ev_hp[kHp] = {nullptr, nullptr};
   uint8_t* h_in = nullptr;
   size_t h_in_cap = 0;
   uint8_t* h_out = nullptr;

@@ -473,8 +473,13 @@ struct Planner {
         // wide-group classes of the other forms.
         const ClassRef* ku = (!wide_G && use_ua && ukeys[ord[i]] >= 0) ? f32_class_of_len(2, (int)lens[ord[i]]) : nullptr;
         if (ku) {
-          const int ngu = 32 / ku->G;
-          if (nr - i < ngu) ku = nullptr;
+          // fewer reads left than the class has lane groups: the all-uniform class that is cheapest per read
+          // served, if the leftover fills every group of it (e.g. 4 reads -> G=8); else the other forms' wide classes
+          if (nr - i < 32 / ku->G) {
+            ku = select_class_for(false, 2, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
+            if (ku && nr - i < 32 / ku->G) ku = nullptr;
+          }
+          const int ngu = ku ? 32 / ku->G : 0;
           for (int32_t x = 1; ku && x < ngu; ++x)
             if (ukeys[ord[i + x]] != ukeys[ord[i]]) ku = nullptr;
         }

@@ -328,6 +328,7 @@ def main():
         e2e_tot = float(tt.item())
     e2e_cells = batch.cells * (world if world > 1 else 1)
     e2e_value = e2e_cells * args.steps / e2e_tot / 1e9
+    e2e_ms = np.array(e2e_t) * 1e3
     assert np.array_equal(ra.out, out), "e2e and resident results differ"
     sampler.stop_flag.set()
     sampler.join(timeout=2)
@@ -352,6 +353,7 @@ def main():
                        "timing": "CUDA events on the library's launching stream around the kernels of each step, summed; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st["h2d_bytes"] // args.steps),
                     "d2h_bytes_per_step": int(st["d2h_bytes"] // args.steps), "ms_per_step": e2e_tot / args.steps * 1e3,
+                    "ms_min_median_max_rank0": [float(e2e_ms.min()), float(np.median(e2e_ms)), float(e2e_ms.max())],
                     "call": "fcs_pairhmm_compute(handle, regions, n_regions): pack from caller pointers -> pinned staging -> H2D -> kernels -> D2H -> scatter"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "fp32_fma", "achieved": main_gcups, "peak": peak_gcups, "unit": UNIT, "frac": main_gcups / peak_gcups,

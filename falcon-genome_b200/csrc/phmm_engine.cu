@@ -1228,7 +1228,7 @@ int Engine::compute_one(const Input& in) {
     tl_text += buf;
   };
   // ---- size every region once
-  std::vector<uint64_t> rc_cells((size_t)n), rc_pairs((size_t)n), rc_bytes((size_t)n);
+  std::vector<uint64_t> rc_cells((size_t)n), rc_pairs((size_t)n), rc_bytes((size_t)n), rc_ub_in((size_t)n);
   for (int64_t g = 0; g < n; ++g) {
     int32_t nr = 0, nh = 0;
     in.shape(g, nr, nh);
@@ -1238,6 +1238,9 @@ int Engine::compute_one(const Input& in) {
     rc_cells[(size_t)g] = sr * sh;
     rc_pairs[(size_t)g] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
     rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
+    // upper bound of the region's share of a chunk's input section: padded planes + metadata + one task and
+    // one striped-path entry per pair at worst
+    rc_ub_in[(size_t)g] = 5 * sr + 91ull * (uint64_t)std::max(0, nr) + sh + 23ull * (uint64_t)std::max(0, nh) + 24ull * rc_pairs[(size_t)g];
   }
   // ---- regions -> devices
   std::vector<std::vector<int64_t>> part(D);
@@ -1303,6 +1306,27 @@ int Engine::compute_one(const Input& in) {
     }
     if (!cur.empty()) chunks.emplace_back(std::move(cur));
     work[d].threads = (int)std::min<size_t>({(size_t)pack_threads_, chunks.size(), devs_[d]->slots.size() / 2});
+    // Which thread gets which chunk is decided at run time, so any slot may receive the largest chunk: give
+    // every slot of the call room for it now.  Growing a slot later means cudaFreeHost + cudaHostAlloc +
+    // cudaFree + cudaMalloc in the middle of the pipeline (measured: calls of 4-700 ms instead of 1.6 ms
+    // until all eight slots had met the largest chunk).  A shortfall (striped-path scratch) is still handled
+    // by the worker's own ensure_buffers.
+    {
+      size_t need_in = 0, need_out = 0, need_tot = 0;
+      for (const auto& ch : chunks) {
+        uint64_t ub = 0, prs = 0;
+        for (int64_t g : ch) { ub += rc_ub_in[(size_t)g]; prs += rc_pairs[(size_t)g]; }
+        const size_t in_b = (size_t)ub + 8192, out_b = (size_t)prs * 13 + 4096;
+        need_in = std::max(need_in, in_b);
+        need_out = std::max(need_out, out_b);
+        need_tot = std::max(need_tot, in_b + (size_t)prs * 8 + out_b + 8192);
+      }
+      if (cudaSetDevice(devs_[d]->ordinal) != cudaSuccess) return set_error(FCS_PHMM_ECUDA, "cudaSetDevice failed");
+      for (int sidx = 0; sidx < 2 * work[d].threads; ++sidx) {
+        const int rc = ensure_buffers(devs_[d]->slots[(size_t)sidx], need_in, need_out, need_tot);
+        if (rc != FCS_PHMM_OK) return rc;
+      }
+    }
     for (int w = 0; w < work[d].threads; ++w) jobs.emplace_back((int)d, w);
     n_jobs += work[d].threads;
   }

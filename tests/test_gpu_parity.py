@@ -202,7 +202,7 @@ def test_golden_fixtures(hmm):
     flags, FP64 reruns to 1e-9, everything within the 1e-4 contract of the double-precision value."""
     from helpers import load_golden, parse_kat
 
-    for name in ("c1_sample.npz", "c5_sample.npz"):
+    for name in ("c1_sample.npz", "c2_sample.npz", "c5_sample.npz"):
         b, z = load_golden(name)
         out, used, raw = hmm.compute_flat(b, want_raw=True)
         assert np.array_equal(used, z["used_fp64"])

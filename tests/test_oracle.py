@@ -100,7 +100,7 @@ def test_simd_port_ftz_mode_agrees(oracle):
 
 
 def test_golden_fixtures_match_oracle(oracle):
-    for name in ("c1_sample.npz", "c5_sample.npz"):
+    for name in ("c1_sample.npz", "c2_sample.npz", "c5_sample.npz"):
         b, z = load_golden(name)
         out, used, raw, dbl = oracle.batch_scalar(b)
         assert np.array_equal(out, z["out_log10"]) and np.array_equal(used, z["used_fp64"])

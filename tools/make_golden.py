@@ -63,6 +63,15 @@ def main():
         read_bases=b5.read_bases, read_q=b5.read_q, read_i=b5.read_i, read_d=b5.read_d, read_c=b5.read_c, rd_off=b5.rd_off, rd_len=b5.rd_len,
         hap_bases=b5.hap_bases, hp_off=b5.hp_off, hp_len=b5.hp_len, reg_read0=b5.reg_read0, reg_nreads=b5.reg_nreads, reg_hap0=b5.reg_hap0,
         reg_nhaps=b5.reg_nhaps, reg_out0=b5.reg_out0, out_log10=out, used_fp64=used, raw_f32_bits=raw.view(np.uint32), log10_double=dbl)
+    # config-2 sample: constant, equal insertion/deletion qualities -> the all-uniform kernels (big enough that the
+    # batcher leaves the latency policy and the tail window: 5120 pairs)
+    b2 = synth.config2_uniform(n_regions=8, reads_per_region=64, haps_per_region=10, read_len=100, hap_len=120, seed=2002)
+    out, used, raw, dbl = O.batch_scalar(b2)
+    np.savez_compressed(
+        os.path.join(GOLD, "c2_sample.npz"),
+        read_bases=b2.read_bases, read_q=b2.read_q, read_i=b2.read_i, read_d=b2.read_d, read_c=b2.read_c, rd_off=b2.rd_off, rd_len=b2.rd_len,
+        hap_bases=b2.hap_bases, hp_off=b2.hp_off, hp_len=b2.hp_len, reg_read0=b2.reg_read0, reg_nreads=b2.reg_nreads, reg_hap0=b2.reg_hap0,
+        reg_nhaps=b2.reg_nhaps, reg_out0=b2.reg_out0, out_log10=out, used_fp64=used, raw_f32_bits=raw.view(np.uint32), log10_double=dbl)
     print("golden written:", sorted(os.listdir(GOLD)), "c1 pairs", b.n_pairs, "fp64", int(used.sum()))
 
 

@@ -476,8 +476,14 @@ struct Planner {
           // fewer reads left than the class has lane groups: the all-uniform class that is cheapest per read
           // served, if the leftover fills every group of it (e.g. 4 reads -> G=8); else the other forms' wide classes
           if (nr - i < 32 / ku->G) {
+            const TierKernel* main_tk = ku->tk;
             ku = select_class_for(false, 2, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
             if (ku && nr - i < 32 / ku->G) ku = nullptr;
+            // a slightly taller class that lives in the kernel of the region's main class saves a launch (and
+            // its fork/join: ~25 us of driver calls per chunk) for a row or two of padding
+            for (int up = 0; ku && ku->tk != main_tk && up <= 3; ++up)
+              if (const ClassRef* alt = find_class(false, 2, ku->G, ku->R + up))
+                if (alt->tk == main_tk) ku = alt;
           }
           const int ngu = ku ? 32 / ku->G : 0;
           for (int32_t x = 1; ku && x < ngu; ++x)
@@ -852,6 +858,9 @@ static void set_gcp_constants(KParams& p, int key) {
 // Enqueue one chunk on the slot's stream.  upload/download = include the H2D / D2H copies.
 int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   const ChunkPlan& P = s.plan;
+  static const bool lc_probe = env_i64("FCS_PHMM_TIMELINE", 0) >= 2;  // developer probe: host cost of the driver calls
+  const double lc0 = lc_probe ? now_ms() : 0;
+  double lc1 = 0, lc2 = 0, lc3 = 0;
   if (upload && P.in_bytes) {
     CK(cudaMemcpyAsync(s.d_buf, s.h_in, P.in_bytes, cudaMemcpyHostToDevice, s.stream));
     stats_.h2d += P.in_bytes;
@@ -859,6 +868,7 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   if (!upload && !P.force_double)  // resident batch: the queues must start empty on every run
     CK(cudaMemsetAsync(s.d_buf + P.off_rcount, 0, kMaxF64Classes * sizeof(uint32_t), s.stream));
   CK(cudaEventRecord(s.ev_k0, s.stream));
+  if (lc_probe) lc1 = now_ms();
   // Fork: launch i goes to stream i % (1 + kSide); the side streams start after the upload and are
   // joined before the next phase, so launches of different classes fill each other's tails.
   // (only the side streams that get a launch are forked and joined: every call here is a driver round
@@ -939,17 +949,24 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
     CK(join(nl));
   }
   CK(cudaEventRecord(s.ev_k1, s.stream));
+  if (lc_probe) lc2 = now_ms();
   {
     const int nl = (int)P.f64.size() + (P.gen64_cap ? 1 : 0);
     int li = 0;
     static const bool f64_prio = env_i64("FCS_PHMM_F64_PRIO", 1) != 0;  // developer knob
-    const bool hp = f64_prio && upload && nl > 0;  // (resident batches run alone: nothing to overtake)
-    const int n_hp = std::min(nl, (int)Slot::kHp);
-    auto pick64 = [&](int i) { return hp ? s.hp[i % Slot::kHp] : pick(i, nl); };
+    // (resident batches run alone: nothing to overtake; one or two launches -- the usual wide + throughput
+    // drain of one tier pair, of which only one has work -- go to the chunk's own stream back to back: the
+    // fork/join around them costs more host time than their overlap saves)
+    static const int f64_serial = (int)env_i64("FCS_PHMM_F64_SERIAL", 2);  // developer knob: 0 off, 1 own stream, 2 one high-priority stream
+    const bool serial64 = f64_serial == 1 && upload && nl <= 2;
+    const bool one_hp = f64_serial == 2 && upload && nl <= 2;
+    const bool hp = f64_prio && upload && nl > 0 && !serial64;
+    const int n_hp = one_hp ? std::min(nl, 1) : std::min(nl, (int)Slot::kHp);
+    auto pick64 = [&](int i) { return serial64 ? s.stream : (hp ? s.hp[one_hp ? 0 : i % Slot::kHp] : pick(i, nl)); };
     if (hp) {
       CK(cudaEventRecord(s.ev_fork, s.stream));
       for (int i = 0; i < n_hp; ++i) CK(cudaStreamWaitEvent(s.hp[i], s.ev_fork, 0));
-    } else {
+    } else if (!serial64) {
       CK(fork(nl));
     }
     if (P.gen64_cap) {
@@ -988,17 +1005,21 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
         CK(cudaEventRecord(s.ev_hp[i], s.hp[i]));
         CK(cudaStreamWaitEvent(s.stream, s.ev_hp[i], 0));
       }
-    } else {
+    } else if (!serial64) {
       CK(join(nl));
     }
   }
   CK(cudaEventRecord(s.ev_k2, s.stream));
+  if (lc_probe) lc3 = now_ms();
   if (download && P.n_pairs) {
     const size_t nbytes = P.total_bytes - P.off_out;
     CK(cudaMemcpyAsync(s.h_out, s.d_buf + P.off_out, nbytes, cudaMemcpyDeviceToHost, s.stream));
     stats_.d2h += nbytes;
   }
   CK(cudaEventRecord(s.ev_done, s.stream));
+  if (lc_probe)
+    fprintf(stderr, "[fcs_phmm launch_chunk, us] h2d+ev %.1f  fp32 phase (%zu launches) %.1f  fp64 phase (%zu launches) %.1f  d2h+ev %.1f\n", (lc1 - lc0) * 1e3,
+            P.f32.size(), (lc2 - lc1) * 1e3, P.f64.size(), (lc3 - lc2) * 1e3, (now_ms() - lc3) * 1e3);
   return FCS_PHMM_OK;
 }
 

@@ -209,7 +209,8 @@ def test_golden_fixtures(hmm):
         assert np.array_equal(raw.view(np.uint32), z["raw_f32_bits"])
         assert np.abs(out - z["log10_double"]).max() <= TOL
         assert np.abs(out - z["out_log10"]).max() <= 4e-6
-        assert np.abs(out[used == 1] - z["out_log10"][used == 1]).max() <= 1e-9
+        if (used == 1).any():
+            assert np.abs(out[used == 1] - z["out_log10"][used == 1]).max() <= 1e-9
     for read, hap, exp in parse_kat():
         assert abs(hmm.compute_likelihoods([read], [hap])[0, 0] - exp) < 5e-6
 

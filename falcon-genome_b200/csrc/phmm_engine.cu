@@ -57,18 +57,22 @@ static int64_t env_i64(const char* name, int64_t dflt) {
 
 // class lookup by read length (hot in the planner: one lookup per read)
 static std::vector<const ClassRef*> g_f32_by_len[3];  // [form]
+static std::vector<const ClassRef*> g_f32_coarse_by_len[3];
 static std::vector<int16_t> g_qid_by_len;             // FP64 queue id
 static std::once_flag g_cls_once;
 static void build_len_tables() {
   for (int form = 0; form < 3; ++form) {
     g_f32_by_len[form].assign(1025, nullptr);
     for (int len = 1; len <= 1024; ++len) g_f32_by_len[form][len] = select_class(false, form, len);
+    g_f32_coarse_by_len[form].assign(1025, nullptr);
+    for (int len = 1; len <= 1024; ++len) g_f32_coarse_by_len[form][len] = select_class(false, form, len, true);
   }
   g_qid_by_len.assign(1025, -1);
   for (int len = 1; len <= 1024; ++len)
     if (const ClassRef* k = select_class(true, false, len)) g_qid_by_len[len] = (int16_t)f64_queue_id(k->G, k->R);
 }
 static inline const ClassRef* f32_class_of_len(int form, int len) { return (len >= 1 && len <= 1024) ? g_f32_by_len[form][len] : nullptr; }
+static inline const ClassRef* f32_coarse_class_of_len(int form, int len) { return (len >= 1 && len <= 1024) ? g_f32_coarse_by_len[form][len] : nullptr; }
 static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid_by_len[len] : -1; }
 
 // The value all qualities of one plane of a read share (masked & 127 like the kernels), or -1.
@@ -301,6 +305,8 @@ struct Planner {
   uint32_t hs_cols;  // haplotype columns per task (bounds the shared-memory stream)
   int sm_count = 148;
   bool shape_tail = true;  // false for every chunk of a call but the last one on its device: their tails overlap the next chunk
+  bool coarse_classes = true;  // unpopular read lengths round up to the coarse class grid (off for resident batches: one launch set, no chunk overlap)
+  std::vector<uint8_t> fine_len;  // per read length: bit `form` set = keep the exact class (bit 0 also covers the uniform-GCP form)
 
   int run(const std::vector<int64_t>& regions, size_t first, size_t& next) {
     ChunkPlan& P = s.plan;
@@ -348,6 +354,9 @@ struct Planner {
     // (instruction cache, 8-CTA/SM footprint) than its faster loop gains (measured on config 3: -7 %).
     std::vector<int> all_gcp, all_ukey;
     bool ua_chunk = false;
+    // reads per fine class (keyed by the general-form class of the length: the forms share the (G, R) grid
+    // closely enough for a popularity test)
+    std::vector<uint32_t> len_hist(1025, 0);
     {
       uint64_t n_elig = 0, n_tot = 0;
       for (size_t kk = first; kk < regions.size(); ++kk) {
@@ -370,11 +379,37 @@ struct Planner {
           all_gcp.push_back(gq);
           all_ukey.push_back(uk);
           n_elig += uk >= 0;
+          if (r.len >= 1 && r.len <= 1024) ++len_hist[(size_t)r.len];
         }
         n_tot += (uint64_t)nr;
       }
       static const bool ua_enabled = env_i64("FCS_PHMM_NO_UA", 0) == 0;  // developer knob: disable the all-uniform kernels
       ua_chunk = ua_enabled && n_elig * 2 >= n_tot && n_tot > 0;
+      // A read length keeps its exact ("fine") class only if that class is popular in this chunk; the
+      // other lengths round up to the coarse grid of rows per lane (phmm_registry.cpp: fewer distinct loop
+      // bodies in flight).  Popular = at least 1/16 of the chunk's reads fall into the class.
+      static const bool coarse_enabled = env_i64("FCS_PHMM_NO_COARSE", 0) == 0;  // developer knob
+      fine_len.assign(1025, (coarse_classes && coarse_enabled) ? 0 : 0xff);
+      if (coarse_classes && coarse_enabled) {
+        for (int form = 0; form < 3; form += 2) {  // general/uniform-GCP grid, all-uniform grid
+          std::vector<std::pair<const ClassRef*, uint64_t>> pop;
+          for (int len = 1; len <= 1024; ++len) {
+            if (!len_hist[(size_t)len]) continue;
+            const ClassRef* kf = f32_class_of_len(form, len);
+            if (!kf) continue;
+            bool found = false;
+            for (auto& pr : pop)
+              if (pr.first == kf) { pr.second += len_hist[(size_t)len]; found = true; break; }
+            if (!found) pop.emplace_back(kf, len_hist[(size_t)len]);
+          }
+          for (int len = 1; len <= 1024; ++len) {
+            if (!len_hist[(size_t)len]) continue;
+            const ClassRef* kf = f32_class_of_len(form, len);
+            for (const auto& pr : pop)
+              if (pr.first == kf && pr.second * 16 >= n_tot) fine_len[(size_t)len] |= (uint8_t)(1u << form);
+          }
+        }
+      }
     }
     static const double tail1_x = (double)env_i64("FCS_PHMM_TAIL1_X100", 150) / 100.0;  // in waves: half-length tasks
     static const double tail2_x = (double)env_i64("FCS_PHMM_TAIL2_X100", 50) / 100.0;   // in waves: wide lane groups, one haplotype
@@ -465,19 +500,21 @@ struct Planner {
         }
         // full groups of the longest remaining read use the table; the last, partly filled group of a
         // region asks for the class that is cheapest per read actually served
-        const ClassRef* k0 = f32_class_of_len(false, (int)lens[ord[i]]);
+        const int len0 = (int)lens[ord[i]];
+        const bool fine0 = len0 > 1024 || (fine_len[(size_t)len0] & 1u), fine2 = len0 > 1024 || (fine_len[(size_t)len0] & 4u);
+        const ClassRef* k0 = fine0 ? f32_class_of_len(0, len0) : f32_coarse_class_of_len(0, len0);
         if (wide_G) k0 = select_class_wide(false, false, (int)lens[ord[i]], wide_G);
-        else if (nr - i < 32 / k0->G) k0 = select_class_for(false, false, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
+        else if (nr - i < 32 / k0->G) k0 = select_class_for(false, false, len0, nr - i, (int)(sum_h / (uint64_t)nh), !fine0);
         // All-uniform form: a full warp of reads that share one (continuation, insertion, deletion)
         // quality triple.  Throughput policy only; leftover groups and latency-bound calls keep the
         // wide-group classes of the other forms.
-        const ClassRef* ku = (!wide_G && use_ua && ukeys[ord[i]] >= 0) ? f32_class_of_len(2, (int)lens[ord[i]]) : nullptr;
+        const ClassRef* ku = (!wide_G && use_ua && ukeys[ord[i]] >= 0) ? (fine2 ? f32_class_of_len(2, len0) : f32_coarse_class_of_len(2, len0)) : nullptr;
         if (ku) {
           // fewer reads left than the class has lane groups: the all-uniform class that is cheapest per read
           // served, if the leftover fills every group of it (e.g. 4 reads -> G=8); else the other forms' wide classes
           if (nr - i < 32 / ku->G) {
             const TierKernel* main_tk = ku->tk;
-            ku = select_class_for(false, 2, (int)lens[ord[i]], nr - i, (int)(sum_h / (uint64_t)nh));
+            ku = select_class_for(false, 2, len0, nr - i, (int)(sum_h / (uint64_t)nh), !fine2);
             if (ku && nr - i < 32 / ku->G) ku = nullptr;
             // a slightly taller class that lives in the kernel of the region's main class saves a launch (and
             // its fork/join: ~25 us of driver calls per chunk) for a row or two of padding
@@ -1494,7 +1531,7 @@ int Engine::batch_create(const fcs_phmm_flat_batch* fb, int device_index, Batch*
   std::iota(regs.begin(), regs.end(), (int64_t)0);
   size_t next = 0;
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
-  Planner pl{*b->input, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count};
+  Planner pl{*b->input, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count, true, false};  // resident: one launch set, exact classes
   int rc = pl.run(regs, 0, next);
   if (rc == FCS_PHMM_OK && next != regs.size())
     rc = set_error(FCS_PHMM_EUNSUPPORTED, "batch too large for one resident chunk (2^31 pairs / 2 GiB of reads+haplotypes)");

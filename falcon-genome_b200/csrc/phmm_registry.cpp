@@ -3,6 +3,7 @@
 #include "phmm_registry.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -21,6 +22,12 @@ inline int fidx(bool f64, int form) { return (f64 ? kForms : 0) + form; }
 constexpr int kMaxSelLen = 1024;
 std::vector<ClassRef> g_classes[2 * kForms];    // [fidx(f64, form)]
 std::vector<const ClassRef*> g_sel[2 * kForms];  // by read length
+std::vector<const ClassRef*> g_sel_coarse[2 * kForms];  // same, restricted to the coarse grid of rows per lane
+// Coarse grid: rows per lane up to 8, then multiples of 4.  A ragged chunk that spreads its reads over every
+// row count runs dozens of different unrolled loop bodies at once (several chunks and tiers are in flight):
+// config 3 end to end went from 1.6 to 2.2 TCUPS on the coarse grid although the tiles sweep ~5 % more
+// cells.  The batcher therefore uses a fine class only for read lengths that are popular in the chunk.
+inline bool on_coarse_grid(int R) { return R <= 8 || (R % 4) == 0; }
 std::vector<std::pair<int, int>> g_f64_queues;  // (G, R) of the general-form FP64 classes
 std::once_flag g_once;
 
@@ -53,6 +60,17 @@ void build() {
       }
       g_sel[f][len] = best;
     }
+    g_sel_coarse[f].assign(kMaxSelLen + 1, nullptr);
+    for (int len = 1; len <= kMaxSelLen; ++len) {
+      const ClassRef* best = nullptr;
+      double bc = 0;
+      for (const ClassRef& k : g_classes[f]) {
+        if (k.G * k.R < len + 1 || !on_coarse_grid(k.R)) continue;
+        const double c = class_cost(f >= kForms, k.G, k.R);
+        if (!best || c < bc) { best = &k; bc = c; }
+      }
+      g_sel_coarse[f][len] = best ? best : g_sel[f][len];
+    }
   }
   for (const ClassRef& k : g_classes[fidx(true, 0)]) g_f64_queues.emplace_back(k.G, k.R);
   for (int f = 0; f < 2 * kForms; ++f) {
@@ -70,22 +88,22 @@ const TierKernel* const* tier_kernels(int* n) {
   return g_kernels;
 }
 
-const ClassRef* select_class(bool f64, int form, int read_len) {
+const ClassRef* select_class(bool f64, int form, int read_len, bool coarse) {
   std::call_once(g_once, build);
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
-  return g_sel[fidx(f64, form)][read_len];
+  return (coarse ? g_sel_coarse : g_sel)[fidx(f64, form)][read_len];
 }
 
-const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, int avg_hap_len) {
+const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, int avg_hap_len, bool coarse) {
   std::call_once(g_once, build);
   if (read_len < 1 || read_len > kMaxSelLen) return nullptr;
   // memo: the choice depends on the haplotype length only weakly -> four length bins; benign races
   // (every thread computes the same pointer)
-  static std::atomic<const ClassRef*> memo[2 * kForms][kMaxSelLen + 1][8][4];
+  static std::atomic<const ClassRef*> memo[2][2 * kForms][kMaxSelLen + 1][8][4];
   const int nb = n_reads < 1 ? 1 : (n_reads > 7 ? 7 : n_reads);
   const int hb = avg_hap_len < 150 ? 0 : (avg_hap_len < 300 ? 1 : (avg_hap_len < 600 ? 2 : 3));
   static const int hb_len[4] = {100, 220, 420, 900};
-  std::atomic<const ClassRef*>& slot = memo[fidx(f64, form)][read_len][nb][hb];
+  std::atomic<const ClassRef*>& slot = memo[coarse ? 1 : 0][fidx(f64, form)][read_len][nb][hb];
   if (const ClassRef* hit = slot.load(std::memory_order_relaxed)) return hit;
   n_reads = nb;
   avg_hap_len = hb_len[hb];
@@ -93,7 +111,7 @@ const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, 
   double bc = 0;
   const double lh = avg_hap_len > 0 ? avg_hap_len : 300;
   for (const ClassRef& k : g_classes[fidx(f64, form)]) {
-    if (k.G * k.R < read_len + 1) continue;
+    if (k.G * k.R < read_len + 1 || (coarse && !on_coarse_grid(k.R))) continue;
     const int served = std::min(n_reads, 32 / k.G);
     const double c = step_cost(f64, k.R) * (lh + k.G - 1) / served;
     if (!best || c < bc * 0.999) { best = &k; bc = c; }

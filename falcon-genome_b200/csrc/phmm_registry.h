@@ -38,10 +38,11 @@ struct ClassRef {
 const TierKernel* const* tier_kernels(int* n);
 // Cheapest class covering a read of this length (rows needed = len + 1) when every lane group of the
 // warp is filled, or nullptr.
-const ClassRef* select_class(bool f64, int form, int read_len);
+// coarse: only classes on the coarse grid of rows per lane (<= 8, then multiples of 4)
+const ClassRef* select_class(bool f64, int form, int read_len, bool coarse = false);
 // Cheapest class per read served when only n_reads (>= 1) reads are left to fill the 32/G lane groups
 // against haplotypes of about avg_hap_len columns: favours wide groups (large G, small R) for leftovers.
-const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, int avg_hap_len);
+const ClassRef* select_class_for(bool f64, int form, int read_len, int n_reads, int avg_hap_len, bool coarse = false);
 const ClassRef* find_class(bool f64, int form, int G, int R);
 // Latency policy (under-filled calls): the class with at least min_G lanes per read and the fewest rows
 // per lane that covers the read -- the shortest serial chain per haplotype column.

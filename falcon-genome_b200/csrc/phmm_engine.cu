@@ -387,8 +387,9 @@ struct Planner {
       ua_chunk = ua_enabled && n_elig * 2 >= n_tot && n_tot > 0;
       // A read length keeps its exact ("fine") class only if that class is popular in this chunk; the
       // other lengths round up to the coarse grid of rows per lane (phmm_registry.cpp: fewer distinct loop
-      // bodies in flight).  Popular = at least 1/16 of the chunk's reads fall into the class.
+      // bodies in flight).  Popular = at least 1/8 of the chunk's reads fall into the class.
       static const bool coarse_enabled = env_i64("FCS_PHMM_NO_COARSE", 0) == 0;  // developer knob
+      static const uint64_t pop_div = (uint64_t)env_i64("FCS_PHMM_POP_DIV", 8);  // developer knob: popular = 1/pop_div of the reads
       fine_len.assign(1025, (coarse_classes && coarse_enabled) ? 0 : 0xff);
       if (coarse_classes && coarse_enabled) {
         for (int form = 0; form < 3; form += 2) {  // general/uniform-GCP grid, all-uniform grid
@@ -406,7 +407,7 @@ struct Planner {
             if (!len_hist[(size_t)len]) continue;
             const ClassRef* kf = f32_class_of_len(form, len);
             for (const auto& pr : pop)
-              if (pr.first == kf && pr.second * 16 >= n_tot) fine_len[(size_t)len] |= (uint8_t)(1u << form);
+              if (pr.first == kf && pr.second * pop_div >= n_tot) fine_len[(size_t)len] |= (uint8_t)(1u << form);
           }
         }
       }

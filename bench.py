@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--threads", type=int, default=0,
+                    help="host packing threads per rank (the library's max_threads, GATK's --native-pair-hmm-threads); "
+                         "0 = this rank's share of the host cores, at most the library default of 4")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="how the timed steps are kept from re-using inputs out of L2: rotate over resident batches whose "
                          "total size exceeds L2 (default), or write a 192 MiB buffer between steps")
@@ -244,7 +247,11 @@ def main():
         torch.cuda.synchronize()
 
     batch, desc = make_workload(args.workload, rank)
-    hmm = PairHMM(devices=[dev_index])
+    # One rank per GPU shares the box's host cores with the other ranks: more packing threads than the rank's
+    # share of cores only makes them (and the event waits) fight for the same cores.
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    pack_threads = args.threads if args.threads > 0 else max(1, min(4, host_threads() // max(1, local_world)))
+    hmm = PairHMM(devices=[dev_index], max_threads=pack_threads)
     res = [hmm.resident(batch, 0)]
     launches_per_step = res[0].launches
     flush = None
@@ -348,7 +355,7 @@ def main():
             "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (+f64 rerun)", "data": "synthetic",
             "config": {"workload": desc, "pairs_per_step_per_gpu": batch.n_pairs, "cells_per_step_per_gpu": batch.cells,
-                       "fp64_rerun_pairs": fp64_pairs, "l2": l2_note,
+                       "fp64_rerun_pairs": fp64_pairs, "l2": l2_note, "host_pack_threads_per_rank": pack_threads,
                        "parallelism": f"{max(world, args.gpus)} x independent region shards, no collective",
                        "timing": "CUDA events on the library's launching stream around the kernels of each step, summed; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st["h2d_bytes"] // args.steps),

@@ -22,6 +22,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
+
+#include <sched.h>
 
 #include "phmm_capture.h"
 #include "phmm_luts.h"
@@ -143,10 +146,8 @@ int Engine::init(const fcs_phmm_config* cfg) {
   if (cfg) std::memcpy(&c, cfg, std::min<size_t>(sizeof(c), cfg->struct_size ? cfg->struct_size : sizeof(c)));
   use_double_ = c.use_double != 0;
   keep_raw_ = c.keep_raw_f32 != 0;
-  pack_threads_ = c.max_threads > 0 ? c.max_threads : (int)env_i64("FCS_PHMM_PACK_THREADS", 4);
+  pack_threads_ = c.max_threads > 0 ? c.max_threads : (int)env_i64("FCS_PHMM_PACK_THREADS", 0);
   max_chunk_cells_ = c.max_chunk_cells > 0 ? c.max_chunk_cells : env_i64("FCS_PHMM_CHUNK_CELLS", 0);  // 0 = adaptive
-  // two slots per packing thread: a thread packs into one while its previous chunk is on the device
-  int nslots = std::max(c.slots_per_device > 0 ? c.slots_per_device : 0, 2 * pack_threads_);
   if (const char* cap = std::getenv("FCS_PHMM_CAPTURE")) {
     int rc = set_capture(cap);
     if (rc != FCS_PHMM_OK) return rc;
@@ -163,6 +164,17 @@ int Engine::init(const fcs_phmm_config* cfg) {
   } else {
     for (int i = 0; i < ndev; ++i) ords.push_back(i);
   }
+  if (pack_threads_ <= 0) {
+    // Default: GATK's --native-pair-hmm-threads default of 4 per device, but never more threads than this
+    // process has cores for.  Oversubscribed packing threads and their event waits fight for the same cores
+    // (measured with 2 cores per GPU: 4 threads 3.7, 2 threads 5.3 TCUPS end to end on two GPUs).
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    pack_threads_ = std::max(1, std::min(4, cores / std::max<int>(1, (int)ords.size())));
+  }
+  // two slots per packing thread: a thread packs into one while its previous chunk is on the device
+  const int nslots = std::max(c.slots_per_device > 0 ? c.slots_per_device : 0, 2 * pack_threads_);
   const Luts& L = luts();
   for (int ord : ords) {
     if (ord < 0 || ord >= ndev) return set_error(FCS_PHMM_EINVAL, "device ordinal out of range");

@@ -94,7 +94,7 @@ typedef struct {
   int32_t n_devices;          /* 0 = every visible device */
   const int32_t* devices;     /* n_devices CUDA ordinals, or NULL for 0..n_devices-1 */
   int32_t use_double;         /* GKL initNative(use_double): force the double path for every pair */
-  int32_t max_threads;        /* GKL initNative(max_threads): host packing threads per device (0 = default 4) */
+  int32_t max_threads;        /* GKL initNative(max_threads): host packing threads per device (0 = default: 4, or fewer if this process has fewer than 4 cores per device) */
   int32_t slots_per_device;   /* in-flight chunk pipelines (streams) per device; at least 2 per packing thread */
   int64_t max_chunk_cells;    /* split a call into chunks of about this many DP cells, 0 = default */
   int32_t keep_raw_f32;       /* 1 = also return the raw float sums through fcs_pairhmm_compute_flat (tests) */

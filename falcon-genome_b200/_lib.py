@@ -112,6 +112,7 @@ CLIENT_SIGNATURES = {
     "fcs_pairhmm_remote_compute_flat": (C.c_int, [C.c_void_p, C.POINTER(FlatStruct), f64p, u8p]),
     "fcs_pairhmm_remote_last_error": (C.c_char_p, [C.c_void_p]),
     "fcs_pairhmm_remote_close": (None, [C.c_void_p]),
+    "fcs_pairhmm_remote_uses_shm": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

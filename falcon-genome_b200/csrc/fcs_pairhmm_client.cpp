@@ -1,20 +1,41 @@
 // libfcs_pairhmm_client — CUDA-free client of the fcs-pairhmm-nam daemon (protocol in fcs_pairhmm_nam.cpp).
 // What a JVM-side shim links when the GPUs are owned by the daemon instead of by the JVM itself.
+#include <algorithm>
 #include <cerrno>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/socket.h>
+#include <sys/syscall.h>
 #include <sys/un.h>
 #include <unistd.h>
 
 #include "../../include/fcs_pairhmm.h"
+#include "phmm_shm.h"
+
+#ifndef MFD_CLOEXEC
+#define MFD_CLOEXEC 0x0001U
+#endif
+#ifndef MFD_ALLOW_SEALING
+#define MFD_ALLOW_SEALING 0x0002U
+#endif
+#ifndef F_ADD_SEALS
+#define F_ADD_SEALS 1033
+#define F_SEAL_SHRINK 0x0002
+#define F_SEAL_GROW 0x0004
+#endif
 
 struct fcs_phmm_remote {
   int fd;
   std::string err;
+  bool shm = true;          // shared-memory transport (phmm_shm.h); false: byte-stream protocol
+  uint8_t* seg = nullptr;   // this connection's segment, mapped here and in the daemon
+  size_t seg_bytes = 0;
 };
 static thread_local std::string g_cerr;
 
@@ -45,6 +66,205 @@ static bool wr(int fd, const void* p, size_t n) {
   return true;
 }
 
+// ---- shared-memory transport (layout and doorbells: phmm_shm.h) -----------------------------------
+using fcsphmm::ShmHeader;
+using fcsphmm::shm_align;
+
+static bool read_reply(fcs_phmm_remote* r, int32_t& rc, uint64_t& n) {
+  uint32_t rs = 0;
+  return rd(r->fd, &rs, 4) && rs == 0x53524850u && rd(r->fd, &rc, 4) && rd(r->fd, &n, 8);
+}
+
+// A segment of at least `need` bytes, known to the daemon.  false: the shared path is unusable (r->shm is
+// cleared, the caller falls back to the byte stream) or the connection is gone (r->err set).
+static bool ensure_segment(fcs_phmm_remote* r, size_t need, bool& conn_lost) {
+  conn_lost = false;
+  if (r->seg && r->seg_bytes >= need) return true;
+  const size_t bytes = (size_t)shm_align(std::max<size_t>(need + need / 2, (size_t)1 << 20));
+  const int mfd = (int)::syscall(SYS_memfd_create, "fcs-pairhmm-client", MFD_CLOEXEC | MFD_ALLOW_SEALING);
+  if (mfd < 0 || ::ftruncate(mfd, (off_t)bytes) != 0 || ::fcntl(mfd, F_ADD_SEALS, F_SEAL_SHRINK | F_SEAL_GROW) != 0) {
+    if (mfd >= 0) ::close(mfd);
+    r->shm = false;
+    return false;
+  }
+  void* m = ::mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, mfd, 0);
+  if (m == MAP_FAILED) {
+    ::close(mfd);
+    r->shm = false;
+    return false;
+  }
+  // doorbell with the descriptor attached
+  uint8_t msg[12];
+  const uint32_t tag = fcsphmm::kShmAttach;
+  const uint64_t b64 = bytes;
+  std::memcpy(msg, &tag, 4);
+  std::memcpy(msg + 4, &b64, 8);
+  iovec iov{msg, sizeof(msg)};
+  alignas(cmsghdr) char ctl[CMSG_SPACE(sizeof(int))];
+  std::memset(ctl, 0, sizeof(ctl));
+  msghdr mh;
+  std::memset(&mh, 0, sizeof(mh));
+  mh.msg_iov = &iov;
+  mh.msg_iovlen = 1;
+  mh.msg_control = ctl;
+  mh.msg_controllen = sizeof(ctl);
+  cmsghdr* cm = CMSG_FIRSTHDR(&mh);
+  cm->cmsg_level = SOL_SOCKET;
+  cm->cmsg_type = SCM_RIGHTS;
+  cm->cmsg_len = CMSG_LEN(sizeof(int));
+  std::memcpy(CMSG_DATA(cm), &mfd, sizeof(int));
+  ssize_t sent;
+  do sent = ::sendmsg(r->fd, &mh, MSG_NOSIGNAL); while (sent < 0 && errno == EINTR);
+  ::close(mfd);  // the mappings keep the memory alive
+  int32_t rc = 0;
+  uint64_t n = 0;
+  if (sent != (ssize_t)sizeof(msg) || !read_reply(r, rc, n)) {
+    ::munmap(m, bytes);
+    r->err = "connection to the PairHMM daemon lost while attaching the shared segment";
+    conn_lost = true;
+    return false;
+  }
+  if (rc != FCS_PHMM_OK) {  // the daemon declined (its text follows): use the byte stream from now on
+    std::string txt((size_t)n, '\0');
+    if (n) rd(r->fd, &txt[0], (size_t)n);
+    ::munmap(m, bytes);
+    r->shm = false;
+    return false;
+  }
+  if (r->seg) ::munmap(r->seg, r->seg_bytes);
+  r->seg = static_cast<uint8_t*>(m);
+  r->seg_bytes = bytes;
+  return true;
+}
+
+// 0 = done through the segment (rc in `result`), 1 = not possible, use the byte stream.
+static int compute_via_shm(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64, int& result) {
+  uint64_t n_reads = 0, n_haps = 0, pairs = 0, read_bytes = 0, hap_bytes = 0;
+  for (int64_t g = 0; g < b->n_regions; ++g) {
+    const int32_t nr = b->reg_nreads[g], nh = b->reg_nhaps[g];
+    if (nr < 0 || nh < 0) { r->err = "negative read or haplotype count"; result = FCS_PHMM_EINVAL; return 0; }
+    if (b->reg_out0[g] != (int64_t)pairs) {
+      r->err = "remote compute needs a dense output layout (reg_out0 = running sum of pairs)";
+      result = FCS_PHMM_EINVAL;
+      return 0;
+    }
+    pairs += (uint64_t)nr * (uint64_t)nh;
+    for (int32_t i = 0; i < nr; ++i) {
+      const int32_t len = b->rd_len[(int64_t)b->reg_read0[g] + i];
+      if (len < 0) { r->err = "negative read length"; result = FCS_PHMM_EINVAL; return 0; }
+      read_bytes += (uint64_t)len;
+    }
+    for (int32_t j = 0; j < nh; ++j) {
+      const int32_t len = b->hp_len[(int64_t)b->reg_hap0[g] + j];
+      if (len < 0) { r->err = "negative haplotype length"; result = FCS_PHMM_EINVAL; return 0; }
+      hap_bytes += (uint64_t)len;
+    }
+    n_reads += (uint64_t)nr;
+    n_haps += (uint64_t)nh;
+  }
+  if (n_reads > 0x7fffffffULL || n_haps > 0x7fffffffULL) return 1;
+  ShmHeader h;
+  std::memset(&h, 0, sizeof(h));
+  h.magic = fcsphmm::kShmMagic;
+  h.version = fcsphmm::kShmVersion;
+  h.n_regions = b->n_regions;
+  h.n_reads = (int64_t)n_reads;
+  h.n_haps = (int64_t)n_haps;
+  h.n_pairs = pairs;
+  h.read_bytes = read_bytes;
+  h.hap_bytes = hap_bytes;
+  uint64_t off = shm_align(sizeof(ShmHeader));
+  auto section = [&](uint64_t bytes) { const uint64_t o = off; off = shm_align(off + bytes); return o; };
+  h.off_read_bases = section(read_bytes);
+  h.off_read_q = section(read_bytes);
+  h.off_read_i = section(read_bytes);
+  h.off_read_d = section(read_bytes);
+  h.off_read_c = section(read_bytes);
+  h.off_rd_off = section(n_reads * 8);
+  h.off_rd_len = section(n_reads * 4);
+  h.off_hap_bases = section(hap_bytes);
+  h.off_hp_off = section(n_haps * 8);
+  h.off_hp_len = section(n_haps * 4);
+  h.off_reg_read0 = section((uint64_t)b->n_regions * 4);
+  h.off_reg_nreads = section((uint64_t)b->n_regions * 4);
+  h.off_reg_hap0 = section((uint64_t)b->n_regions * 4);
+  h.off_reg_nhaps = section((uint64_t)b->n_regions * 4);
+  h.off_out = section(pairs * 8);
+  h.off_used = section(pairs);
+  h.total_bytes = off;
+  bool lost = false;
+  if (!ensure_segment(r, (size_t)off, lost)) {
+    if (lost) { result = FCS_PHMM_ENODEV; return 0; }
+    return 1;
+  }
+  uint8_t* s = r->seg;
+  int64_t* rd_off = reinterpret_cast<int64_t*>(s + h.off_rd_off);
+  int32_t* rd_len = reinterpret_cast<int32_t*>(s + h.off_rd_len);
+  int64_t* hp_off = reinterpret_cast<int64_t*>(s + h.off_hp_off);
+  int32_t* hp_len = reinterpret_cast<int32_t*>(s + h.off_hp_len);
+  int32_t* g_r0 = reinterpret_cast<int32_t*>(s + h.off_reg_read0);
+  int32_t* g_nr = reinterpret_cast<int32_t*>(s + h.off_reg_nreads);
+  int32_t* g_h0 = reinterpret_cast<int32_t*>(s + h.off_reg_hap0);
+  int32_t* g_nh = reinterpret_cast<int32_t*>(s + h.off_reg_nhaps);
+  uint64_t rpos = 0, hpos = 0, ri = 0, hi = 0;
+  for (int64_t g = 0; g < b->n_regions; ++g) {  // reads and haplotypes re-indexed densely, in region order
+    const int32_t nr = b->reg_nreads[g], nh = b->reg_nhaps[g];
+    g_r0[g] = (int32_t)ri;
+    g_nr[g] = nr;
+    g_h0[g] = (int32_t)hi;
+    g_nh[g] = nh;
+    for (int32_t i = 0; i < nr; ++i, ++ri) {
+      const int64_t k = (int64_t)b->reg_read0[g] + i, o = b->rd_off[k];
+      const size_t len = (size_t)b->rd_len[k];
+      rd_off[ri] = (int64_t)rpos;
+      rd_len[ri] = (int32_t)len;
+      std::memcpy(s + h.off_read_bases + rpos, b->read_bases + o, len);
+      std::memcpy(s + h.off_read_q + rpos, b->read_q + o, len);
+      std::memcpy(s + h.off_read_i + rpos, b->read_i + o, len);
+      std::memcpy(s + h.off_read_d + rpos, b->read_d + o, len);
+      std::memcpy(s + h.off_read_c + rpos, b->read_c + o, len);
+      rpos += len;
+    }
+    for (int32_t j = 0; j < nh; ++j, ++hi) {
+      const int64_t k = (int64_t)b->reg_hap0[g] + j;
+      const size_t len = (size_t)b->hp_len[k];
+      hp_off[hi] = (int64_t)hpos;
+      hp_len[hi] = (int32_t)len;
+      std::memcpy(s + h.off_hap_bases + hpos, b->hap_bases + b->hp_off[k], len);
+      hpos += len;
+    }
+  }
+  std::memcpy(s, &h, sizeof(h));
+  uint8_t bell[12];
+  const uint32_t tag = fcsphmm::kShmRequest;
+  const uint64_t zero = 0;
+  std::memcpy(bell, &tag, 4);
+  std::memcpy(bell + 4, &zero, 8);
+  int32_t rc = 0;
+  uint64_t n = 0;
+  if (!wr(r->fd, bell, sizeof(bell)) || !read_reply(r, rc, n)) {
+    r->err = "connection to the PairHMM daemon lost";
+    result = FCS_PHMM_ENODEV;
+    return 0;
+  }
+  if (rc != FCS_PHMM_OK) {
+    std::string msg((size_t)n, '\0');
+    if (n) rd(r->fd, &msg[0], (size_t)n);
+    r->err = "daemon: " + msg;
+    result = rc;
+    return 0;
+  }
+  if (n != pairs) {
+    r->err = "daemon returned an unexpected number of pairs";
+    result = FCS_PHMM_EINVAL;
+    return 0;
+  }
+  std::memcpy(out, s + h.off_out, (size_t)pairs * sizeof(double));
+  if (used_fp64) std::memcpy(used_fp64, s + h.off_used, (size_t)pairs);
+  result = FCS_PHMM_OK;
+  return 0;
+}
+
 extern "C" {
 
 FCS_PHMM_API int fcs_pairhmm_remote_open(const char* socket_path, fcs_phmm_remote** out) {
@@ -60,21 +280,32 @@ FCS_PHMM_API int fcs_pairhmm_remote_open(const char* socket_path, fcs_phmm_remot
     if (fd >= 0) ::close(fd);
     return FCS_PHMM_ENODEV;
   }
-  *out = new fcs_phmm_remote{fd, ""};
+  fcs_phmm_remote* r = new fcs_phmm_remote();
+  r->fd = fd;
+  if (const char* e = std::getenv("FCS_PHMM_REMOTE_SHM")) r->shm = std::atoi(e) != 0;
+  *out = r;
   return FCS_PHMM_OK;
 }
 
 FCS_PHMM_API void fcs_pairhmm_remote_close(fcs_phmm_remote* r) {
   if (!r) return;
+  if (r->seg) ::munmap(r->seg, r->seg_bytes);
   ::close(r->fd);
   delete r;
 }
+
+/* 1 while requests travel through the shared segment, 0 on the byte-stream protocol. */
+FCS_PHMM_API int fcs_pairhmm_remote_uses_shm(const fcs_phmm_remote* r) { return r && r->shm ? 1 : 0; }
 
 FCS_PHMM_API const char* fcs_pairhmm_remote_last_error(const fcs_phmm_remote* r) { return r ? r->err.c_str() : g_cerr.c_str(); }
 
 // Same contract as fcs_pairhmm_compute_flat, executed by the daemon.
 FCS_PHMM_API int fcs_pairhmm_remote_compute_flat(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64) {
   if (!r || !b || !out) return FCS_PHMM_EINVAL;
+  if (r->shm) {
+    int result = FCS_PHMM_OK;
+    if (compute_via_shm(r, b, out, used_fp64, result) == 0) return result;
+  }
   std::vector<uint8_t> buf;
   auto w32 = [&](uint32_t v) {
     const uint8_t* q = reinterpret_cast<const uint8_t*>(&v);

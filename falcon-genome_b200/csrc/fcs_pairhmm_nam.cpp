@@ -15,6 +15,9 @@
 //   request : u32 'PHRQ', u64 payload bytes, payload = one capture block ('RBLK' ..., phmm_capture.h)
 //   response: u32 'PHRS', i32 rc, u64 n;  rc == 0: n pairs -> n doubles then n flag bytes;
 //                                          rc <  0: n bytes of error text
+// Shared-memory transport (the default of libfcs_pairhmm_client; layout, doorbells and trust rules in
+// phmm_shm.h): the client attaches a sealed memfd segment ('PHSM' + descriptor), writes each batch into it and
+// rings 'PHSQ'; the daemon scores the batch in place and writes the results into the segment.
 #include <atomic>
 #include <cerrno>
 #include <csignal>
@@ -25,12 +28,20 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/un.h>
 #include <unistd.h>
 
 #include "../../include/fcs_pairhmm.h"
+#include "phmm_shm.h"
+
+#ifndef F_GET_SEALS
+#define F_GET_SEALS 1034
+#define F_SEAL_SHRINK 0x0002
+#endif
 
 static std::atomic<bool> g_stop{false};
 static int g_listen_fd = -1;
@@ -66,14 +77,182 @@ static bool write_all(int fd, const void* p, size_t n) {
   return true;
 }
 
+// Reads n bytes; a descriptor that arrives as ancillary data of those bytes is returned in *got_fd
+// (a plain read() would silently drop it).
+static bool read_with_fd(int fd, void* p, size_t n, int* got_fd) {
+  uint8_t* b = static_cast<uint8_t*>(p);
+  while (n) {
+    iovec iov{b, n};
+    alignas(cmsghdr) char ctl[CMSG_SPACE(sizeof(int) * 4)];
+    msghdr mh;
+    std::memset(&mh, 0, sizeof(mh));
+    mh.msg_iov = &iov;
+    mh.msg_iovlen = 1;
+    mh.msg_control = ctl;
+    mh.msg_controllen = sizeof(ctl);
+    ssize_t r = ::recvmsg(fd, &mh, MSG_CMSG_CLOEXEC);
+    if (r <= 0) {
+      if (r < 0 && errno == EINTR) continue;
+      return false;
+    }
+    for (cmsghdr* cm = CMSG_FIRSTHDR(&mh); cm; cm = CMSG_NXTHDR(&mh, cm)) {
+      if (cm->cmsg_level != SOL_SOCKET || cm->cmsg_type != SCM_RIGHTS) continue;
+      const size_t nfd = (cm->cmsg_len - CMSG_LEN(0)) / sizeof(int);
+      for (size_t i = 0; i < nfd; ++i) {
+        int f;
+        std::memcpy(&f, CMSG_DATA(cm) + i * sizeof(int), sizeof(int));
+        if (*got_fd < 0) *got_fd = f;
+        else ::close(f);
+      }
+    }
+    b += r;
+    n -= (size_t)r;
+  }
+  return true;
+}
+
+static bool reply(int fd, int32_t rc, uint64_t n, const char* text) {
+  const uint32_t rs = 0x53524850u;  // PHRS
+  bool ok = write_all(fd, &rs, 4) && write_all(fd, &rc, 4);
+  if (rc == FCS_PHMM_OK) return ok && write_all(fd, &n, 8);
+  const uint64_t m = std::strlen(text);
+  return ok && write_all(fd, &m, 8) && write_all(fd, text, m);
+}
+
+// A client's segment as mapped here, and the private copies of its index arrays.
+struct Segment {
+  uint8_t* p = nullptr;
+  size_t bytes = 0;
+  std::vector<int64_t> rd_off, hp_off, reg_out0;
+  std::vector<int32_t> rd_len, hp_len, reg_read0, reg_nreads, reg_hap0, reg_nhaps;
+  void unmap() {
+    if (p) ::munmap(p, bytes);
+    p = nullptr;
+    bytes = 0;
+  }
+  ~Segment() { unmap(); }
+};
+
+// Maps the descriptor a client sent.  The segment must be sealed against shrinking: a client that truncates
+// the file under a live mapping would otherwise turn the daemon's next access into SIGBUS.
+static const char* attach_segment(Segment& sg, int mfd, uint64_t claimed) {
+  struct stat st;
+  if (mfd < 0) return "attach request without a descriptor";
+  if (::fstat(mfd, &st) != 0 || (uint64_t)st.st_size < claimed || claimed < sizeof(fcsphmm::ShmHeader)) return "segment smaller than announced";
+  const int seals = ::fcntl(mfd, F_GET_SEALS);
+  if (seals < 0 || !(seals & F_SEAL_SHRINK)) return "segment is not sealed against shrinking (memfd with F_SEAL_SHRINK required)";
+  void* m = ::mmap(nullptr, (size_t)claimed, PROT_READ | PROT_WRITE, MAP_SHARED, mfd, 0);
+  if (m == MAP_FAILED) return "cannot map the segment";
+  sg.unmap();
+  sg.p = static_cast<uint8_t*>(m);
+  sg.bytes = (size_t)claimed;
+  return nullptr;
+}
+
+// Validates the batch in the segment and builds the flat view: bulk bytes stay in the segment, every index
+// goes through a private copy.  Returns an error text or nullptr.
+static const char* view_segment(Segment& sg, fcs_phmm_flat_batch& b, fcsphmm::ShmHeader& h) {
+  if (!sg.p) return "no segment attached";
+  std::memcpy(&h, sg.p, sizeof(h));
+  if (h.magic != fcsphmm::kShmMagic || h.version != fcsphmm::kShmVersion) return "bad segment header";
+  const uint64_t lim = 0x7fffffffULL;
+  if (h.n_regions < 0 || h.n_reads < 0 || h.n_haps < 0 || (uint64_t)h.n_regions > lim || (uint64_t)h.n_reads > lim ||
+      (uint64_t)h.n_haps > lim || h.read_bytes > sg.bytes || h.hap_bytes > sg.bytes || h.n_pairs > sg.bytes)
+    return "segment header counts out of range";
+  auto inside = [&](uint64_t off, uint64_t bytes, uint64_t align) {
+    return off % align == 0 && off <= sg.bytes && bytes <= sg.bytes - off;
+  };
+  const uint64_t nr = (uint64_t)h.n_reads, nh = (uint64_t)h.n_haps, ng = (uint64_t)h.n_regions;
+  if (!inside(h.off_read_bases, h.read_bytes, 1) || !inside(h.off_read_q, h.read_bytes, 1) || !inside(h.off_read_i, h.read_bytes, 1) ||
+      !inside(h.off_read_d, h.read_bytes, 1) || !inside(h.off_read_c, h.read_bytes, 1) || !inside(h.off_hap_bases, h.hap_bytes, 1) ||
+      !inside(h.off_rd_off, nr * 8, 8) || !inside(h.off_rd_len, nr * 4, 4) || !inside(h.off_hp_off, nh * 8, 8) ||
+      !inside(h.off_hp_len, nh * 4, 4) || !inside(h.off_reg_read0, ng * 4, 4) || !inside(h.off_reg_nreads, ng * 4, 4) ||
+      !inside(h.off_reg_hap0, ng * 4, 4) || !inside(h.off_reg_nhaps, ng * 4, 4) || !inside(h.off_out, h.n_pairs * 8, 8) ||
+      !inside(h.off_used, h.n_pairs, 1))
+    return "segment section outside the mapping";
+  auto copy = [&](auto& v, uint64_t off, uint64_t n) {
+    v.resize((size_t)n);
+    if (n) std::memcpy(v.data(), sg.p + off, (size_t)n * sizeof(v[0]));
+  };
+  copy(sg.rd_off, h.off_rd_off, nr);
+  copy(sg.rd_len, h.off_rd_len, nr);
+  copy(sg.hp_off, h.off_hp_off, nh);
+  copy(sg.hp_len, h.off_hp_len, nh);
+  copy(sg.reg_read0, h.off_reg_read0, ng);
+  copy(sg.reg_nreads, h.off_reg_nreads, ng);
+  copy(sg.reg_hap0, h.off_reg_hap0, ng);
+  copy(sg.reg_nhaps, h.off_reg_nhaps, ng);
+  for (uint64_t k = 0; k < nr; ++k)
+    if (sg.rd_len[k] < 0 || sg.rd_off[k] < 0 || (uint64_t)sg.rd_off[k] > h.read_bytes || (uint64_t)sg.rd_len[k] > h.read_bytes - (uint64_t)sg.rd_off[k])
+      return "read outside its plane";
+  for (uint64_t k = 0; k < nh; ++k)
+    if (sg.hp_len[k] < 0 || sg.hp_off[k] < 0 || (uint64_t)sg.hp_off[k] > h.hap_bytes || (uint64_t)sg.hp_len[k] > h.hap_bytes - (uint64_t)sg.hp_off[k])
+      return "haplotype outside its plane";
+  sg.reg_out0.resize((size_t)ng);
+  uint64_t pairs = 0;
+  for (uint64_t g = 0; g < ng; ++g) {
+    const int64_t r0 = sg.reg_read0[g], n_r = sg.reg_nreads[g], h0 = sg.reg_hap0[g], n_h = sg.reg_nhaps[g];
+    if (r0 < 0 || n_r < 0 || h0 < 0 || n_h < 0 || (uint64_t)(r0 + n_r) > nr || (uint64_t)(h0 + n_h) > nh) return "region outside the read or haplotype tables";
+    sg.reg_out0[g] = (int64_t)pairs;
+    pairs += (uint64_t)n_r * (uint64_t)n_h;
+    if (pairs > h.n_pairs) return "regions hold more pairs than the header announces";
+  }
+  if (pairs != h.n_pairs) return "pair count of the regions differs from the header";
+  std::memset(&b, 0, sizeof(b));
+  b.read_bases = sg.p + h.off_read_bases;
+  b.read_q = sg.p + h.off_read_q;
+  b.read_i = sg.p + h.off_read_i;
+  b.read_d = sg.p + h.off_read_d;
+  b.read_c = sg.p + h.off_read_c;
+  b.rd_off = sg.rd_off.data();
+  b.rd_len = sg.rd_len.data();
+  b.n_reads = h.n_reads;
+  b.hap_bases = sg.p + h.off_hap_bases;
+  b.hp_off = sg.hp_off.data();
+  b.hp_len = sg.hp_len.data();
+  b.n_haps = h.n_haps;
+  b.reg_read0 = sg.reg_read0.data();
+  b.reg_nreads = sg.reg_nreads.data();
+  b.reg_hap0 = sg.reg_hap0.data();
+  b.reg_nhaps = sg.reg_nhaps.data();
+  b.reg_out0 = sg.reg_out0.data();
+  b.n_regions = h.n_regions;
+  return nullptr;
+}
+
 static void serve(int fd, fcs_phmm_handle* h) {
   std::vector<uint8_t> payload;
   std::vector<double> out;
   std::vector<uint8_t> used;
+  Segment sg;
   for (;;) {
     uint32_t magic = 0;
     uint64_t len = 0;
-    if (!read_all(fd, &magic, 4) || magic != 0x51524850u /* PHRQ */ || !read_all(fd, &len, 8) || len > (1ull << 32)) break;
+    int mfd = -1;
+    if (!read_with_fd(fd, &magic, 4, &mfd) || !read_with_fd(fd, &len, 8, &mfd)) {
+      if (mfd >= 0) ::close(mfd);
+      break;
+    }
+    if (magic == fcsphmm::kShmAttach) {
+      const char* err = attach_segment(sg, mfd, len);
+      if (mfd >= 0) ::close(mfd);
+      if (!reply(fd, err ? FCS_PHMM_EINVAL : FCS_PHMM_OK, 0, err ? err : "")) break;
+      continue;
+    }
+    if (mfd >= 0) ::close(mfd);
+    if (magic == fcsphmm::kShmRequest) {
+      fcs_phmm_flat_batch b;
+      fcsphmm::ShmHeader sh;
+      const char* err = view_segment(sg, b, sh);
+      int32_t rc = err ? FCS_PHMM_EINVAL : FCS_PHMM_OK;
+      if (!err) {
+        rc = fcs_pairhmm_compute_flat(h, &b, reinterpret_cast<double*>(sg.p + sh.off_out), sg.p + sh.off_used, nullptr);
+        if (rc != FCS_PHMM_OK) err = fcs_pairhmm_last_error(h);
+      }
+      if (!reply(fd, rc, err ? 0 : sh.n_pairs, err ? err : "")) break;
+      continue;
+    }
+    if (magic != 0x51524850u /* PHRQ */ || len > (1ull << 32)) break;
     payload.resize((size_t)len);
     if (!read_all(fd, payload.data(), payload.size())) break;
     fcs_phmm_flat_batch b;

@@ -810,7 +810,7 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
       std::memcpy(dst, h.b, (size_t)h.len);
       std::memset(dst + h.len, 'N', lp - (uint32_t)h.len);
       uint8_t ok = 1;
-      for (int32_t x = 0; x < h.len; ++x) ok &= valid[h.b[x]];
+      for (int32_t x = 0; x < h.len; ++x) ok &= valid[dst[x]];  // the copy, not the source: the caller's memory may be shared (daemon segment)
       if (!ok) return set_error(FCS_PHMM_EINVAL, "haplotype contains a byte outside ACGTN");
       hmeta[hidx].data_off16 = (uint32_t)(hpos / 16);
       hmeta[hidx].len = (uint32_t)h.len;

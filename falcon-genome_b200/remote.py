@@ -38,6 +38,11 @@ class RemotePairHMM:
             raise PairHMMError(rc, (self._lib.fcs_pairhmm_remote_last_error(self._h) or b"").decode())
         return out, used
 
+    @property
+    def uses_shm(self) -> bool:
+        """True while requests go through the shared-memory segment, False on the byte-stream protocol."""
+        return bool(self._lib.fcs_pairhmm_remote_uses_shm(self._h))
+
     def close(self):
         if self._h:
             self._lib.fcs_pairhmm_remote_close(self._h)

@@ -219,12 +219,16 @@ FCS_PHMM_API int fcs_pairhmm_finalize_region(double* log10_likelihoods, int32_t 
 /* ---- service seam: client of the fcs-pairhmm-nam daemon -----------------
  * The daemon (falcon-genome_b200/csrc/fcs_pairhmm_nam.cpp) owns the GPUs for the lifetime of a stage, as the
  * Blaze NAM does in the reference (src/worker-htc.cpp:99-112, src/BackgroundExecutor.cpp:13-84).  These
- * four symbols live in libfcs_pairhmm_client.so, which has no CUDA dependency. */
+ * symbols live in libfcs_pairhmm_client.so, which has no CUDA dependency. */
 typedef struct fcs_phmm_remote fcs_phmm_remote;
 FCS_PHMM_API int fcs_pairhmm_remote_open(const char* socket_path, fcs_phmm_remote** out);
 FCS_PHMM_API int fcs_pairhmm_remote_compute_flat(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64);
 FCS_PHMM_API const char* fcs_pairhmm_remote_last_error(const fcs_phmm_remote* r);
 FCS_PHMM_API void fcs_pairhmm_remote_close(fcs_phmm_remote* r);
+/* 1 while requests travel through the connection's shared-memory segment (the default; the batch is written
+ * once into a sealed memfd that the daemon maps, csrc/phmm_shm.h), 0 on the byte-stream protocol
+ * (FCS_PHMM_REMOTE_SHM=0, or a daemon that declined the segment). */
+FCS_PHMM_API int fcs_pairhmm_remote_uses_shm(const fcs_phmm_remote* r);
 
 /* ---- introspection ------------------------------------------------------------------ */
 FCS_PHMM_API int fcs_pairhmm_get_stats(fcs_phmm_handle* h, fcs_phmm_stats* out);

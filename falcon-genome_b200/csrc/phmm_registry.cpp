@@ -27,7 +27,10 @@ std::vector<const ClassRef*> g_sel_coarse[2 * kForms];  // same, restricted to t
 // row count runs dozens of different unrolled loop bodies at once (several chunks and tiers are in flight):
 // config 3 end to end went from 1.6 to 2.2 TCUPS on the coarse grid although the tiles sweep ~5 % more
 // cells.  The batcher therefore uses a fine class only for read lengths that are popular in the chunk.
-inline bool on_coarse_grid(int R) { return R <= 8 || (R % 4) == 0; }
+inline bool on_coarse_grid(int R) {
+  static const int step = [] { const char* e = std::getenv("FCS_PHMM_COARSE_STEP"); const int v = e ? std::atoi(e) : 4; return v >= 1 ? v : 4; }();  // developer knob
+  return R <= 8 || (R % step) == 0;
+}
 std::vector<std::pair<int, int>> g_f64_queues;  // (G, R) of the general-form FP64 classes
 std::once_flag g_once;
 

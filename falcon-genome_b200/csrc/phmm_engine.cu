@@ -1213,6 +1213,7 @@ class CombinedInput : public Input {
   double* out(int64_t g) const override { const auto w = where(g); return parts_[w.first]->out(w.second); }
   uint8_t* used(int64_t g) const override { const auto w = where(g); return parts_[w.first]->used(w.second); }
   float* raw(int64_t g) const override { const auto w = where(g); return parts_[w.first]->raw(w.second); }
+  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const override { const auto w = where(g); parts_[w.first]->sum_lens(w.second, sr, sh); }
 
  private:
   std::pair<size_t, int64_t> where(int64_t g) const {
@@ -1304,8 +1305,7 @@ int Engine::compute_one(const Input& in) {
     int32_t nr = 0, nh = 0;
     in.shape(g, nr, nh);
     uint64_t sr = 0, sh = 0;
-    for (int32_t i = 0; i < nr; ++i) sr += (uint64_t)std::max(0, in.read(g, i).len);
-    for (int32_t j = 0; j < nh; ++j) sh += (uint64_t)std::max(0, in.hap(g, j).len);
+    in.sum_lens(g, sr, sh);
     rc_cells[(size_t)g] = sr * sh;
     rc_pairs[(size_t)g] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
     rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
@@ -1513,6 +1513,15 @@ class FlatInput : public Input {
   double* out(int64_t g) const override { return out_ ? out_ + b_.reg_out0[g] : nullptr; }
   uint8_t* used(int64_t g) const override { return used_ ? used_ + b_.reg_out0[g] : nullptr; }
   float* raw(int64_t g) const override { return raw_ ? raw_ + b_.reg_out0[g] : nullptr; }
+  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const override {
+    const int32_t* rl = b_.rd_len + b_.reg_read0[g];
+    const int32_t* hl = b_.hp_len + b_.reg_hap0[g];
+    uint64_t a = 0, b = 0;
+    for (int32_t i = 0; i < b_.reg_nreads[g]; ++i) a += (uint64_t)(rl[i] > 0 ? rl[i] : 0);
+    for (int32_t j = 0; j < b_.reg_nhaps[g]; ++j) b += (uint64_t)(hl[j] > 0 ? hl[j] : 0);
+    sr = a;
+    sh = b;
+  }
 
  private:
   fcs_phmm_flat_batch b_;

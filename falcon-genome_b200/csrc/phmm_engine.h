@@ -42,6 +42,15 @@ class Input {
   virtual double* out(int64_t g) const = 0;
   virtual uint8_t* used(int64_t g) const = 0;
   virtual float* raw(int64_t g) const = 0;
+  // Sum of the (non-negative) read and haplotype lengths of region g: the sizing pass of a call walks every
+  // read once, so inputs override this with a loop over their own arrays (no virtual call per read).
+  virtual void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const {
+    int32_t nr = 0, nh = 0;
+    shape(g, nr, nh);
+    sr = sh = 0;
+    for (int32_t i = 0; i < nr; ++i) { const int32_t l = read(g, i).len; sr += (uint64_t)(l > 0 ? l : 0); }
+    for (int32_t j = 0; j < nh; ++j) { const int32_t l = hap(g, j).len; sh += (uint64_t)(l > 0 ? l : 0); }
+  }
 };
 
 struct F32Range {

@@ -16,6 +16,7 @@
 #include <emmintrin.h>
 #endif
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -103,6 +104,51 @@ static int uniform_gcp(const uint8_t* c, int32_t len) {
 }
 
 static cudaError_t init_slot(Slot& s);
+
+// Cores of the NUMA node a device is attached to (sysfs), restricted to the process's affinity mask.
+static bool device_node_cpus(int ordinal, cpu_set_t* out) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), ordinal) != cudaSuccess) return false;
+  for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+  int node = -1;
+  {
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    std::FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+  }
+  if (node < 0) return false;
+  char list[4096] = {0};
+  {
+    const std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+    std::FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    const bool ok = std::fgets(list, sizeof(list), f) != nullptr;
+    std::fclose(f);
+    if (!ok) return false;
+  }
+  cpu_set_t mine, node_set;
+  CPU_ZERO(&mine);
+  CPU_ZERO(&node_set);
+  if (sched_getaffinity(0, sizeof(mine), &mine) != 0) return false;
+  for (const char* p = list; *p;) {  // "0-15,32-47"
+    char* end = nullptr;
+    long a = std::strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    if (*end == '-') { p = end + 1; b = std::strtol(p, &end, 10); }
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+      if (c >= 0 && CPU_ISSET((int)c, &mine)) CPU_SET((int)c, &node_set);
+    p = (*end == ',') ? end + 1 : end;
+    if (*end != ',') break;
+  }
+  if (CPU_COUNT(&node_set) == 0) return false;
+  *out = node_set;
+  return true;
+}
+
+static thread_local bool t_pool_thread = false;  // set by WorkerPool::loop: only the library's own threads are ever re-bound
 
 int ChunkPlan::launches() const {
   int n = 0;
@@ -201,7 +247,21 @@ int Engine::init(const fcs_phmm_config* cfg) {
       for (int i = 0; i < nk; ++i) CK(tks[i]->set_max_smem(prop.sharedMemPerBlockOptin));
     }
     d->slots.resize(nslots);
-    for (Slot& s : d->slots) CK(init_slot(s));
+    static const bool numa_bind = env_i64("FCS_PHMM_NUMA_BIND", 0) != 0;  // opt-in, see Device::node_cpus
+    cpu_set_t before;
+    bool rebound = false;
+    if (numa_bind && device_node_cpus(ord, &d->node_cpus)) {
+      d->has_node_cpus = true;
+      // allocate the pinned staging from the device's node (first touch happens when the pages are pinned)
+      CPU_ZERO(&before);
+      if (sched_getaffinity(0, sizeof(before), &before) == 0 && sched_setaffinity(0, sizeof(cpu_set_t), &d->node_cpus) == 0) rebound = true;
+      if (env_i64("FCS_PHMM_DEBUG", 0)) fprintf(stderr, "[fcs_phmm] device %d: packing threads bound to %d cores of its NUMA node\n", ord, CPU_COUNT(&d->node_cpus));
+    }
+    cudaError_t slot_err = cudaSuccess;
+    for (Slot& s : d->slots)
+      if ((slot_err = init_slot(s)) != cudaSuccess) break;
+    if (rebound) sched_setaffinity(0, sizeof(before), &before);
+    CK(slot_err);
     devs_.push_back(std::move(d));
   }
   pool_.reset(new WorkerPool(std::max(0, (int)devs_.size() * pack_threads_ - 1)));
@@ -1155,6 +1215,7 @@ void WorkerPool::drain() {
   }
 }
 void WorkerPool::loop() {
+  t_pool_thread = true;
   uint64_t seen = 0;
   for (;;) {
     // Calls arrive back to back (one per active region or per batch): spin briefly for the next one
@@ -1417,6 +1478,7 @@ int Engine::compute_one(const Input& in) {
     DevWork& dw = work[(size_t)jobs[(size_t)job].first];
     const int w = jobs[(size_t)job].second;
     if (cudaSetDevice(d.ordinal) != cudaSuccess) { set_error(FCS_PHMM_ECUDA, "cudaSetDevice failed"); fail_with(FCS_PHMM_ECUDA); return; }
+    if (d.has_node_cpus && t_pool_thread) sched_setaffinity(0, sizeof(cpu_set_t), &d.node_cpus);  // never the caller's own thread
     int use = 0;
     while (first_rc.load() == FCS_PHMM_OK) {
       const size_t c = dw.next.fetch_add(1);

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -142,6 +144,10 @@ struct Device {
   void* d_mm_d = nullptr;
   std::vector<Slot> slots;
   std::mutex mu;  // one call at a time drives a device's slots
+  // FCS_PHMM_NUMA_BIND=1 (opt-in): the cores of the NUMA node the GPU hangs off, intersected with the process's
+  // affinity mask.  Pool threads that work for this device run there and its pinned staging is allocated from there.
+  cpu_set_t node_cpus;
+  bool has_node_cpus = false;
 };
 
 struct Stats {

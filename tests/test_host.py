@@ -169,3 +169,57 @@ def test_planner_picks_the_kernel_form_from_the_qualities():
     minority = [region(16, 150, 45, 45, 10) for _ in range(big // 4)] + [region(16, 150, 45, 40, 10) for _ in range(big)]
     g, u, a = forms(minority)
     assert a == 0 and u > 0
+
+
+# ---- property test of the batcher (hypothesis): any ragged call shape is covered exactly once ----------
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+_read_len = st.one_of(st.integers(1, 24), st.integers(25, 260), st.integers(261, 420), st.integers(384, 1200))
+_hap_len = st.one_of(st.integers(1, 40), st.integers(41, 700), st.integers(1990, 2100))
+
+
+@st.composite
+def _call_shape(draw):
+    regions = []
+    for _ in range(draw(st.integers(1, 12))):
+        reads = draw(st.lists(st.tuples(_read_len, st.sampled_from(["ua", "ug", "general", "ins_ne_del"])), min_size=1, max_size=70))
+        haps = draw(st.lists(st.tuples(_hap_len, st.booleans()), min_size=1, max_size=9))
+        regions.append((reads, haps))
+    return regions
+
+
+@settings(max_examples=40, deadline=None)
+@given(_call_shape(), st.integers(0, 2 ** 31 - 1))
+def test_property_batcher_covers_any_call_shape(shape, seed):
+    """fcs_pairhmm_plan_check (the real planner + packer, host only) accepts any mix of read / haplotype lengths and
+    quality forms -- single-pass classes, the striped path for long reads and long haplotypes, leftover groups,
+    latency mode -- and its own coverage check finds every (read, hap) pair exactly once."""
+    from falcon_genome_b200 import plan_check
+
+    rng = np.random.default_rng(seed)
+    regs = []
+    for reads, haps in shape:
+        rr = []
+        for L, form in reads:
+            ins = bytearray([45] * L)
+            dele = bytearray([45] * L)
+            gcp = bytearray([10] * L)
+            if form in ("ug", "general") and L > 1:
+                ins[int(rng.integers(0, L))] = 30
+                dele = bytearray(ins)
+            if form == "general" and L > 1:
+                gcp[int(rng.integers(0, L))] = 11
+            if form == "ins_ne_del":
+                dele = bytearray([40] * L)
+            rr.append((bytes(rng.choice(list(b"ACGTN"), L).astype(np.uint8)), bytes(rng.integers(2, 42, L).astype(np.uint8)), bytes(ins), bytes(dele),
+                       bytes(gcp)))
+        hh = [bytes(rng.choice(list(b"ACGTN" if with_n else b"ACGT"), L).astype(np.uint8)) for L, with_n in haps]
+        regs.append(Region(rr, hh))
+    b = FlatBatch.from_regions(regs)
+    info = plan_check(b)
+    assert info["n_pairs"] == b.n_pairs
+    assert info["n_tasks"] + info["n_generic_pairs"] > 0
+    assert info["n_tasks"] == info["n_tasks_general"] + info["n_tasks_uniform_gcp"] + info["n_tasks_all_uniform"]
+    assert info["max_smem_bytes"] <= 227 * 1024
+    assert 0.0 < info["geometric_efficiency"] <= 1.0

@@ -157,3 +157,59 @@ def test_independent_full_matrix_forward_at_realistic_size(oracle):
         read = (rs.tobytes(), q.astype(np.uint8).tobytes(), iq.astype(np.uint8).tobytes(), dq.astype(np.uint8).tobytes(), cq.astype(np.uint8).tobytes())
         got = oracle.log10_double(read, hap.tobytes())
         assert abs(got - want) < 1e-9, (Lr, Lh, got, want)
+
+
+# ---- property tests (hypothesis) --------------------------------------------------
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+_BASES = st.sampled_from(list(b"ACGTN"))
+
+
+@st.composite
+def _pair(draw, max_read=6, max_hap=6, qmin=2, qmax=60):
+    lr = draw(st.integers(1, max_read))
+    lh = draw(st.integers(1, max_hap))
+    plane = lambda lo, hi: bytes(draw(st.lists(st.integers(lo, hi), min_size=lr, max_size=lr)))  # noqa: E731
+    read = (bytes(draw(st.lists(_BASES, min_size=lr, max_size=lr))), plane(qmin, qmax), plane(qmin, qmax), plane(qmin, qmax), plane(qmin, 40))
+    hap = bytes(draw(st.lists(_BASES, min_size=lh, max_size=lh)))
+    return read, hap
+
+
+@settings(max_examples=60, deadline=None)
+@given(_pair())
+def test_property_dp_equals_sum_over_all_alignments(oracle, p):
+    """The rolling-array DP equals the explicit enumeration of every alignment path (no DP) for any tiny pair."""
+    read, hap = p
+    assert abs(oracle.log10_double(read, hap) - oracle.bruteforce_log10(read, hap)) < 1e-12
+
+
+@settings(max_examples=60, deadline=None)
+@given(_pair(max_read=40, max_hap=80))
+def test_property_float_first_double_fallback(oracle, p):
+    """GKL's decision rule: the result comes from the double pass exactly when the raw float sum is below 1e-28f;
+    otherwise the float result is within the parity tolerance of the double one.  Likelihoods are probabilities."""
+    read, hap = p
+    v, used, raw = oracle.pair(read, hap)
+    dbl = oracle.log10_double(read, hap)
+    assert used == int(np.float32(raw) < np.float32(1e-28))
+    assert raw == oracle.sum_float(read, hap)
+    if used:
+        assert v == dbl
+    else:
+        assert abs(v - dbl) < 5e-5
+    assert dbl <= 1e-12 and math.isfinite(dbl)
+
+
+@settings(max_examples=40, deadline=None)
+@given(_pair(max_read=30, max_hap=60), st.integers(0, 2 ** 32 - 1))
+def test_property_high_bits_of_qualities_and_n_wildcard(oracle, p, seed):
+    """Qualities are used & 127; replacing a read base by N can only add probability mass."""
+    (bases, q, i, d, c), hap = p
+    rng = np.random.default_rng(seed)
+    hi = lambda x: bytes((np.frombuffer(x, np.uint8) | (rng.integers(0, 2, len(x)).astype(np.uint8) << 7)).tolist())  # noqa: E731
+    base = oracle.log10_double((bases, q, i, d, c), hap)
+    assert oracle.log10_double((bases, hi(q), hi(i), hi(d), hi(c)), hap) == base
+    k = int(rng.integers(0, len(bases)))
+    with_n = bases[:k] + b"N" + bases[k + 1:]
+    assert oracle.log10_double((with_n, q, i, d, c), hap) >= base - 1e-12

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -220,7 +221,18 @@ static const char* view_segment(Segment& sg, fcs_phmm_flat_batch& b, fcsphmm::Sh
   return nullptr;
 }
 
-static void serve(int fd, fcs_phmm_handle* h) {
+// Byte-stream requests are sized by the client: bound what one request may make the daemon allocate.
+static const uint64_t kMaxStreamPayload = 1ull << 31;  // 2 GiB of capture block (the engine's own per-chunk input limit)
+static const uint64_t kMaxPairsPerRequest = 0x7fffffffULL;  // the engine's pair limit per chunk
+
+static bool reply_stream_error(int fd, int32_t rc, const char* msg) {
+  const uint32_t rs = 0x53524850u;  // PHRS
+  const uint64_t m = std::strlen(msg);
+  return write_all(fd, &rs, 4) && write_all(fd, &rc, 4) && write_all(fd, &m, 8) && write_all(fd, msg, m);
+}
+
+// One connection.  Returns when the client closes, the protocol is violated, or a reply cannot be written.
+static void serve_loop(int fd, fcs_phmm_handle* h) {
   std::vector<uint8_t> payload;
   std::vector<double> out;
   std::vector<uint8_t> used;
@@ -243,39 +255,84 @@ static void serve(int fd, fcs_phmm_handle* h) {
     if (magic == fcsphmm::kShmRequest) {
       fcs_phmm_flat_batch b;
       fcsphmm::ShmHeader sh;
-      const char* err = view_segment(sg, b, sh);
-      int32_t rc = err ? FCS_PHMM_EINVAL : FCS_PHMM_OK;
-      if (!err) {
-        rc = fcs_pairhmm_compute_flat(h, &b, reinterpret_cast<double*>(sg.p + sh.off_out), sg.p + sh.off_used, nullptr);
-        if (rc != FCS_PHMM_OK) err = fcs_pairhmm_last_error(h);
+      const char* err = nullptr;
+      int32_t rc = FCS_PHMM_OK;
+      try {
+        err = view_segment(sg, b, sh);
+        rc = err ? FCS_PHMM_EINVAL : FCS_PHMM_OK;
+        if (!err) {
+          rc = fcs_pairhmm_compute_flat(h, &b, reinterpret_cast<double*>(sg.p + sh.off_out), sg.p + sh.off_used, nullptr);
+          if (rc != FCS_PHMM_OK) err = fcs_pairhmm_last_error(h);
+        }
+      } catch (const std::bad_alloc&) {  // the private index copies of view_segment
+        rc = FCS_PHMM_ENOMEM;
+        err = "daemon out of host memory for this request";
       }
       if (!reply(fd, rc, err ? 0 : sh.n_pairs, err ? err : "")) break;
       continue;
     }
-    if (magic != 0x51524850u /* PHRQ */ || len > (1ull << 32)) break;
-    payload.resize((size_t)len);
-    if (!read_all(fd, payload.data(), payload.size())) break;
+    if (magic != 0x51524850u /* PHRQ */) break;
+    if (len > kMaxStreamPayload) {  // cannot skip that much and stay in sync: answer, then drop the connection
+      reply_stream_error(fd, FCS_PHMM_EINVAL, "request payload larger than the daemon accepts");
+      break;
+    }
     fcs_phmm_flat_batch b;
     void* owner = nullptr;
-    int32_t rc = fcs_pairhmm_capture_parse(payload.data(), payload.size(), &b, &owner);
+    int32_t rc = FCS_PHMM_OK;
     uint64_t n = 0;
-    if (rc == FCS_PHMM_OK) {
-      for (int64_t g = 0; g < b.n_regions; ++g) n += (uint64_t)b.reg_nreads[g] * (uint64_t)b.reg_nhaps[g];
-      out.resize((size_t)n);
-      used.resize((size_t)n);
-      rc = fcs_pairhmm_compute_flat(h, &b, out.data(), used.data(), nullptr);
+    const char* err = nullptr;
+    try {
+      payload.resize((size_t)len);
+      if (!read_all(fd, payload.data(), payload.size())) break;
+      rc = fcs_pairhmm_capture_parse(payload.data(), payload.size(), &b, &owner);
+      if (rc != FCS_PHMM_OK) err = fcs_pairhmm_last_error(h);
+      if (rc == FCS_PHMM_OK) {
+        // zero-length reads / haplotypes cost four payload bytes each, so the pair count is NOT bounded by the
+        // payload size: check it before sizing the result arrays
+        for (int64_t g = 0; g < b.n_regions && n <= kMaxPairsPerRequest; ++g) n += (uint64_t)b.reg_nreads[g] * (uint64_t)b.reg_nhaps[g];
+        if (n > kMaxPairsPerRequest) {
+          rc = FCS_PHMM_EINVAL;
+          err = "request holds more pairs than one call may carry (2^31 - 1)";
+        }
+      }
+      if (rc == FCS_PHMM_OK) {
+        out.resize((size_t)n);
+        used.resize((size_t)n);
+        rc = fcs_pairhmm_compute_flat(h, &b, out.data(), used.data(), nullptr);
+        if (rc != FCS_PHMM_OK) err = fcs_pairhmm_last_error(h);
+      }
+    } catch (const std::bad_alloc&) {
+      rc = FCS_PHMM_ENOMEM;
+      err = "daemon out of host memory for this request";
+    } catch (const std::length_error&) {
+      rc = FCS_PHMM_EINVAL;
+      err = "request too large";
     }
-    const uint32_t rs = 0x53524850u;  // PHRS
-    bool ok = write_all(fd, &rs, 4) && write_all(fd, &rc, 4);
+    bool ok;
     if (rc == FCS_PHMM_OK) {
-      ok = ok && write_all(fd, &n, 8) && write_all(fd, out.data(), n * sizeof(double)) && write_all(fd, used.data(), n);
+      const uint32_t rs = 0x53524850u;  // PHRS
+      ok = write_all(fd, &rs, 4) && write_all(fd, &rc, 4) && write_all(fd, &n, 8) && write_all(fd, out.data(), n * sizeof(double)) &&
+           write_all(fd, used.data(), n);
     } else {
-      const char* msg = fcs_pairhmm_last_error(h);
-      const uint64_t m = std::strlen(msg);
-      ok = ok && write_all(fd, &m, 8) && write_all(fd, msg, m);
+      ok = reply_stream_error(fd, rc, err ? err : "error");
     }
     fcs_pairhmm_capture_free(owner);
     if (!ok) break;
+    if (out.capacity() > (64u << 20)) {  // do not let one large request pin its buffers for the connection's lifetime
+      std::vector<double>().swap(out);
+      std::vector<uint8_t>().swap(used);
+      std::vector<uint8_t>().swap(payload);
+    }
+  }
+}
+
+// Thread body of a connection: nothing a client sends may take the daemon down (it owns the GPUs of every JVM
+// of the stage, /root/reference/src/worker-htc.cpp:99-112); an exception ends this connection only.
+static void serve(int fd, fcs_phmm_handle* h) {
+  try {
+    serve_loop(fd, h);
+  } catch (...) {
+    std::fprintf(stderr, "fcs-pairhmm-nam: connection %d dropped after an internal error\n", fd);
   }
   ::close(fd);
 }
@@ -335,19 +392,22 @@ int main(int argc, char** argv) {
   }
   std::printf("fcs-pairhmm-nam ready on %s with %d device(s)\n", path.c_str(), fcs_pairhmm_device_count(h));
   std::fflush(stdout);
-  std::vector<std::thread> conns;
   while (!g_stop) {
     int fd = ::accept(g_listen_fd, nullptr, nullptr);
     if (fd < 0) {
       if (errno == EINTR) continue;
       break;
     }
-    conns.emplace_back(serve, fd, h);
+    // detached at creation: a connection ends when its client closes, and a long stage with many reconnects
+    // must not accumulate thread handles; the process exits with _exit() below
+    try {
+      std::thread(serve, fd, h).detach();
+    } catch (...) {  // thread creation failed (resource limit): refuse this client, keep serving the others
+      ::close(fd);
+    }
   }
   ::close(g_listen_fd);
   ::unlink(path.c_str());
-  for (auto& t : conns)
-    if (t.joinable()) t.detach();  // connections end when their clients close; the process exits now
   fcs_phmm_stats s;
   if (fcs_pairhmm_get_stats(h, &s) == FCS_PHMM_OK)
     std::printf("fcs-pairhmm-nam stopping: %llu pairs, %llu cells, %llu chunks served\n", (unsigned long long)s.pairs, (unsigned long long)s.cells,

@@ -1205,13 +1205,13 @@ WorkerPool::~WorkerPool() {
   cv_.notify_all();
   for (auto& t : th_) t.join();
 }
-void WorkerPool::drain() {
+void WorkerPool::drain(const std::shared_ptr<Run>& r) {
   for (;;) {
-    const int j = next_.fetch_add(1);
-    if (j >= n_jobs_) break;
-    (*fn_)(j);
+    const int j = r->next.fetch_add(1);
+    if (j >= r->n_jobs) break;  // r->fn is dereferenced only for a job of this very run, which run() is still waiting for
+    (*r->fn)(j);
     std::lock_guard<std::mutex> lk(mu_);
-    if (--pending_ == 0) done_cv_.notify_all();
+    if (--r->pending == 0) done_cv_.notify_all();
   }
 }
 void WorkerPool::loop() {
@@ -1226,30 +1226,33 @@ void WorkerPool::loop() {
       __builtin_ia32_pause();
 #endif
     }
+    std::shared_ptr<Run> r;
     {
       std::unique_lock<std::mutex> lk(mu_);
       cv_.wait(lk, [&] { return stop_ || gen_.load() != seen; });
       if (stop_) return;
       seen = gen_.load();
+      r = cur_;
     }
-    drain();
+    if (r) drain(r);
   }
 }
 void WorkerPool::run(int n_jobs, const std::function<void(int)>& fn) {
   if (n_jobs <= 0) return;
+  auto r = std::make_shared<Run>();
+  r->fn = &fn;
+  r->n_jobs = n_jobs;
+  r->pending = n_jobs;
   {
     std::lock_guard<std::mutex> lk(mu_);
-    fn_ = &fn;
-    n_jobs_ = n_jobs;
-    pending_ = n_jobs;
-    next_.store(0);
+    cur_ = r;
     gen_.fetch_add(1, std::memory_order_release);
   }
   cv_.notify_all();
-  drain();  // the caller works too
+  drain(r);  // the caller works too
   std::unique_lock<std::mutex> lk(mu_);
-  done_cv_.wait(lk, [&] { return pending_ == 0; });
-  n_jobs_ = 0;  // late wakers find nothing to do
+  done_cv_.wait(lk, [&] { return r->pending == 0; });  // every job of THIS run has returned: fn and its captures may go
+  if (cur_ == r) cur_.reset();
 }
 
 // One call: a single pass sizes every region; regions are split over the devices by DP cells
@@ -1292,7 +1295,58 @@ class CombinedInput : public Input {
 // everything queued so far as ONE batch (flat combining).  Results are independent of the batching, so the
 // merge is invisible to the callers; if a merged batch fails, its calls are re-run one by one so that each
 // caller gets its own error.
+// Cheap structural check of a call (pointers and lengths only): what the planner would reject with EINVAL /
+// EUNSUPPORTED, found before anything dereferences the arrays (capture) or a merged batch is formed.
+static int validate_input(const Input& in) {
+  const int64_t n = in.n_regions();
+  if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
+  for (int64_t g = 0; g < n; ++g) {
+    int32_t nr = 0, nh = 0;
+    in.shape(g, nr, nh);
+    if (nr < 0 || nh < 0) return set_error(FCS_PHMM_EINVAL, "negative read or haplotype count");
+    if (nr == 0 || nh == 0) continue;
+    if (!in.out(g)) return set_error(FCS_PHMM_EINVAL, "out_log10 is null");
+    for (int32_t i = 0; i < nr; ++i) {
+      const InRead r = in.read(g, i);
+      if (r.len <= 0 || !r.b || !r.q || !r.i || !r.d || !r.c) return set_error(FCS_PHMM_EINVAL, "read with non-positive length or null array");
+      if (r.len > FCS_PHMM_MAX_READ_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "read longer than FCS_PHMM_MAX_READ_LEN");
+    }
+    for (int32_t j = 0; j < nh; ++j) {
+      const InHap h = in.hap(g, j);
+      if (h.len <= 0 || !h.b) return set_error(FCS_PHMM_EINVAL, "haplotype with non-positive length or null array");
+      if (h.len > FCS_PHMM_MAX_HAP_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype longer than FCS_PHMM_MAX_HAP_LEN");
+    }
+  }
+  return FCS_PHMM_OK;
+}
+
+// compute_one() behind a firewall: nothing thrown on the host side of a batch (std::bad_alloc from the planner's
+// vectors is the realistic case) may leave the flat-combining leader section.
+int Engine::compute_one_noexcept(const Input& in) {
+  try {
+    return compute_one(in);
+  } catch (const std::bad_alloc&) {
+    return set_error(FCS_PHMM_ENOMEM, "host allocation failed");
+  } catch (const std::exception& ex) {
+    return set_error(FCS_PHMM_EINVAL, std::string("internal: ") + ex.what());
+  } catch (...) {
+    return set_error(FCS_PHMM_EINVAL, "internal: unknown exception");
+  }
+}
+
 int Engine::compute(const Input& in) {
+  // Per call, before it can join a batch: structural validation (a malformed call must not fail the callers it
+  // would be merged with) and the capture hook (once per original call, and only for calls that passed the
+  // checks, so the writer never dereferences a null plane).
+  {
+    const int rc = validate_input(in);
+    if (rc != FCS_PHMM_OK) return rc;
+  }
+  if (in.n_regions() == 0) return FCS_PHMM_OK;
+  if (capture_ && capture_->active()) {
+    const int rc = capture_->append(in);
+    if (rc != FCS_PHMM_OK) return rc;
+  }
   PendingCall me;
   me.in = &in;
   std::unique_lock<std::mutex> lk(comb_mu_);
@@ -1304,22 +1358,29 @@ int Engine::compute(const Input& in) {
     }
     comb_leader_ = true;
     std::vector<PendingCall*> batch;
-    batch.swap(comb_queue_);
+    batch.swap(comb_queue_);  // (no allocation: swap)
     lk.unlock();
-    if (batch.size() == 1) {
-      batch[0]->rc = compute_one(*batch[0]->in);
-      if (batch[0]->rc != FCS_PHMM_OK) batch[0]->err = last_error();
-    } else {
-      std::vector<const Input*> parts;
-      for (PendingCall* c : batch) parts.push_back(c->in);
-      CombinedInput all(parts);
-      int rc = compute_one(all);
-      if (rc != FCS_PHMM_OK) {
-        for (PendingCall* c : batch) {
-          c->rc = compute_one(*c->in);
-          if (c->rc != FCS_PHMM_OK) c->err = last_error();
+    // Leader section.  Whatever happens here, every call of the batch is marked done with a result and the
+    // leadership is given up: a caller left waiting would hang its JVM thread for good.
+    try {
+      if (batch.size() == 1) {
+        batch[0]->rc = compute_one_noexcept(*batch[0]->in);
+        if (batch[0]->rc != FCS_PHMM_OK) batch[0]->err = last_error();
+      } else {
+        std::vector<const Input*> parts;
+        for (PendingCall* c : batch) parts.push_back(c->in);
+        CombinedInput all(parts);
+        int rc = compute_one_noexcept(all);
+        if (rc != FCS_PHMM_OK) {
+          for (PendingCall* c : batch) {
+            c->rc = compute_one_noexcept(*c->in);
+            if (c->rc != FCS_PHMM_OK) c->err = last_error();
+          }
         }
       }
+    } catch (...) {  // allocation of `parts` / CombinedInput / an error string
+      for (PendingCall* c : batch)
+        if (c->rc == FCS_PHMM_OK) c->rc = FCS_PHMM_ENOMEM;  // err text stays empty: assigning it could throw again
     }
     lk.lock();
     for (PendingCall* c : batch) c->done = true;
@@ -1327,7 +1388,7 @@ int Engine::compute(const Input& in) {
     comb_cv_.notify_all();
   }
   lk.unlock();
-  if (me.rc != FCS_PHMM_OK) return set_error(me.rc, me.err);
+  if (me.rc != FCS_PHMM_OK) return set_error(me.rc, me.err.empty() ? std::string("host allocation failed") : me.err);
   return FCS_PHMM_OK;
 }
 
@@ -1336,10 +1397,6 @@ int Engine::compute_one(const Input& in) {
   if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
   if (n == 0) return FCS_PHMM_OK;
   std::lock_guard<std::mutex> call_lock(compute_mu_);
-  if (capture_ && capture_->active()) {
-    int rc = capture_->append(in);
-    if (rc != FCS_PHMM_OK) return rc;
-  }
   const size_t D = devs_.size();
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
   static const bool timeline = env_i64("FCS_PHMM_TIMELINE", 0) != 0;  // developer knob: host timeline of the call on stderr
@@ -1474,6 +1531,7 @@ int Engine::compute_one(const Input& in) {
     }
   };
   const std::function<void(int)> worker = [&](int job) {
+   try {
     Device& d = *devs_[(size_t)jobs[(size_t)job].first];
     DevWork& dw = work[(size_t)jobs[(size_t)job].first];
     const int w = jobs[(size_t)job].second;
@@ -1518,6 +1576,17 @@ int Engine::compute_one(const Input& in) {
       if (r2 != FCS_PHMM_OK) fail_with(r2);
       tl_mark("drained", w, (size_t)k);
     }
+   } catch (...) {  // pool threads have no caller to unwind to (std::bad_alloc from the planner's vectors is the realistic case)
+    set_error(FCS_PHMM_ENOMEM, "host allocation failed in a packing thread");
+    fail_with(FCS_PHMM_ENOMEM);
+    // this worker's chunks in flight still point at the caller's arrays: let them finish, then forget them
+    Device& d = *devs_[(size_t)jobs[(size_t)job].first];
+    for (int k = 0; k < 2; ++k) {
+      Slot& s = d.slots[(size_t)2 * jobs[(size_t)job].second + k];
+      if (s.busy) cudaEventSynchronize(s.ev_done);
+      s.busy = false;
+    }
+   }
   };
   if (n_jobs == 1) worker(0);
   else pool_->run(n_jobs, worker);
@@ -1532,8 +1601,12 @@ int Engine::submit(std::unique_ptr<Input> in, std::shared_ptr<void> keepalive, f
   Pending* raw = p.get();
   std::shared_ptr<Input> sin(in.release());
   raw->th = std::thread([this, raw, sin, keepalive] {
-    raw->rc = compute(*sin);
-    if (raw->rc != FCS_PHMM_OK) raw->err = last_error();
+    try {
+      raw->rc = compute(*sin);
+      if (raw->rc != FCS_PHMM_OK) raw->err = last_error();
+    } catch (...) {
+      raw->rc = FCS_PHMM_ENOMEM;
+    }
   });
   std::lock_guard<std::mutex> lk(tickets_mu_);
   *t = next_ticket_++;

@@ -165,14 +165,21 @@ class WorkerPool {
   void run(int n_jobs, const std::function<void(int)>& fn);
 
  private:
+  // One run() call.  Workers snapshot the descriptor under mu_ and keep it alive through the shared_ptr, so a
+  // thread that is late (preempted between taking an index and testing it) only ever compares that index with
+  // the job count of the run it belongs to and can never execute a job of a later run.
+  struct Run {
+    const std::function<void(int)>* fn = nullptr;
+    int n_jobs = 0;
+    int pending = 0;  // guarded by mu_
+    std::atomic<int> next{0};
+  };
   void loop();
-  void drain();
+  void drain(const std::shared_ptr<Run>& r);
   std::vector<std::thread> th_;
   std::mutex mu_;
   std::condition_variable cv_, done_cv_;
-  const std::function<void(int)>* fn_ = nullptr;
-  int n_jobs_ = 0, pending_ = 0;
-  std::atomic<int> next_{0};
+  std::shared_ptr<Run> cur_;  // guarded by mu_
   std::atomic<uint64_t> gen_{0};
   bool stop_ = false;
 };
@@ -186,6 +193,7 @@ class Engine {
   ~Engine();
   int compute(const Input& in);       // coalesces concurrent callers into one device batch
   int compute_one(const Input& in);   // one batch, caller holds the device (compute_mu_)
+  int compute_one_noexcept(const Input& in);
   int submit(std::unique_ptr<Input> in, std::shared_ptr<void> keepalive, fcs_phmm_ticket* t);
   int wait(fcs_phmm_ticket t);
   int batch_create(const fcs_phmm_flat_batch* b, int device_index, Batch** out);

@@ -2,10 +2,11 @@
 // native PairHMM call [upstream GATK4; restated from the published
 // algorithm — none of it is in /root/reference], so that a caller can hand the library raw reads:
 //
-//  before:  base quals capped by the mapping quality, then "q < 18 -> 6"; insertion / deletion quals
-//           default to 45 when the BAM has no BI/BD tags; PCR indel error model: at every base the
-//           tandem-repeat length around it lowers both gap-open quals to
-//           max(10, round(40 - exp(repeatLength / (rateFactor * pi)) + 1)); gap continuation constant 10.
+//  before:  insertion / deletion quals default to 45 when the BAM has no BI/BD tags; PCR indel error model: at
+//           every base the tandem-repeat length around it lowers both gap-open quals to
+//           max(10, round(40 - exp(repeatLength / (rateFactor * pi)) + 1)); then capMinimumReadQualities:
+//           base quals capped by the mapping quality, "q < 18 -> 6", insertion / deletion quals floored at
+//           MIN_USABLE_Q_SCORE (6); gap continuation constant 10.
 //  after:   per read, likelihoods are capped at best + log10(global mismapping rate = 10^-4.5);
 //           reads whose best likelihood is below  min(2, ceil(len * 0.02)) * -4.0  are flagged as
 //           poorly modelled.
@@ -39,7 +40,10 @@ int count_repeats(const uint8_t* unit, int ulen, const uint8_t* seq, int n, bool
   return reps;
 }
 
-// GATK findTandemRepeatUnits(readBases, offset).getRight(): repeat count of the best unit around offset
+// GATK findTandemRepeatUnits(readBases, offset).getRight(): repeat count of the best unit around offset.
+// As published, the best backward / forward unit starts as the single base at offset / offset + 1 and is
+// replaced only by the first unit length whose repeat count exceeds 1 (the assignment sits inside
+// `if (maxBW > 1)`); the count variable keeps the value of the last length tried.
 int tandem_repeat_length(const uint8_t* b, int n, int offset) {
   int max_bw = 0;
   const uint8_t* best_bw = b + offset;
@@ -95,6 +99,13 @@ int prepare_read(const uint8_t* bases, const uint8_t* raw_q, int32_t len, int32_
       out_i[k - 1] = std::min(out_i[k - 1], cache[rl]);
       out_d[k - 1] = std::min(out_d[k - 1], cache[rl]);
     }
+  }
+  // capMinimumReadQualities, second half: after the PCR model (GATK's order: applyPCRErrorModel, then the caps)
+  // insertion and deletion qualities below MIN_USABLE_Q_SCORE are set to it (setToFixedValueIfTooLow(q, 6, 6));
+  // only BAM-supplied BI/BD values can be that low.
+  for (int32_t k = 0; k < len; ++k) {
+    if (out_i[k] < p.min_usable_q) out_i[k] = (uint8_t)p.min_usable_q;
+    if (out_d[k] < p.min_usable_q) out_d[k] = (uint8_t)p.min_usable_q;
   }
   return FCS_PHMM_OK;
 }

@@ -363,6 +363,18 @@ int Engine::ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t de
   return FCS_PHMM_OK;
 }
 
+// haplotype byte classes: 0 = ACGT, bit 0 = N, bit 1 = any other byte
+static const uint8_t* hap_byte_class() {
+  static uint8_t lut[256];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    std::memset(lut, 2, sizeof(lut));
+    lut[(int)'A'] = lut[(int)'C'] = lut[(int)'G'] = lut[(int)'T'] = 0;
+    lut[(int)'N'] = 1;
+  });
+  return lut;
+}
+
 // ---------------------------------------------------------------------------------------
 // Pass 1: choose the regions of the chunk, order each region's reads by length, cut the
 // (read group x haplotype run) tasks per kernel class and size every section.
@@ -390,6 +402,8 @@ struct Planner {
     s.gen_flags.clear();
     uint32_t gen64_cap = 0, gen_maxlh = 0;
     bool any_n = false;  // some haplotype contains an N: the prior table needs its sixth symbol row
+    bool hap_other[256] = {false};  // haplotype bytes outside ACGTN seen in this chunk (GKL compares raw bytes: they are legal input)
+    bool any_other = false;
     // Latency policy for under-filled chunks: if even with one task per (4 reads x 1 haplotype) the chunk
     // cannot fill the one-warp CTA slots of the device, the call is latency bound: the time is the serial
     // chain of one task.  Then give every read the widest lane group (shortest chain per column) that still
@@ -529,7 +543,17 @@ struct Planner {
         if (h.len > FCS_PHMM_MAX_HAP_LEN) return set_error(FCS_PHMM_EUNSUPPORTED, "haplotype longer than FCS_PHMM_MAX_HAP_LEN");
         hlens[j] = (uint32_t)h.len;
         sum_h += (uint64_t)h.len;
-        if (!any_n && std::memchr(h.b, 'N', (size_t)h.len)) any_n = true;
+        {
+          const uint8_t* cls = hap_byte_class();
+          uint8_t seen = 0;
+          for (int32_t x = 0; x < h.len; ++x) seen |= cls[h.b[x]];
+          any_n = any_n || (seen & 1u);
+          if (seen & 2u) {
+            any_other = true;
+            for (int32_t x = 0; x < h.len; ++x)
+              if (cls[h.b[x]] & 2u) hap_other[h.b[x]] = true;
+          }
+        }
         hb += round_up16((uint32_t)h.len);
       }
       const uint64_t cells = sum_r * sum_h;
@@ -666,6 +690,30 @@ struct Planner {
     size_t off = 0;
     P.latency_mode = min_G != 0;
     P.n_sym = any_n ? 6u : 5u;
+    P.extra_bytes = 0;
+    if (any_other) {
+      // Haplotype bytes outside ACGTN match a read base only if the read holds the same byte (or an N).  The ones
+      // no read of the chunk contains share one symbol row; each of the others needs its own.
+      bool shared[256] = {false};
+      uint32_t n_extra = 0;
+      for (int64_t g : P.regions) {
+        int32_t nr = 0, nh = 0;
+        in.shape(g, nr, nh);
+        if (nr <= 0 || nh <= 0) continue;
+        for (int32_t i = 0; i < nr; ++i) {
+          const InRead r = in.read(g, i);
+          for (int32_t x = 0; x < r.len; ++x)
+            if (hap_other[r.b[x]] && !shared[r.b[x]]) {
+              shared[r.b[x]] = true;
+              if (n_extra >= (uint32_t)kMaxExtraSyms)
+                return set_error(FCS_PHMM_EUNSUPPORTED, "more than 8 distinct byte values outside ACGTN occur in both reads and haplotypes of one chunk");
+              P.extra_bytes |= (uint64_t)r.b[x] << (8u * n_extra);
+              ++n_extra;
+            }
+        }
+      }
+      P.n_sym = (uint32_t)kCodeExtra0 + n_extra;
+    }
     P.off_reads = off; off = align_up(off + reads_bytes, 256);
     P.off_haps = off; off = align_up(off + haps_bytes, 256);
     P.off_rmeta = off; off = align_up(off + P.n_reads * sizeof(ReadMeta), 256);
@@ -826,15 +874,6 @@ struct Planner {
 
 }  // namespace
 
-static const uint8_t* hap_valid_lut() {
-  static uint8_t lut[256];
-  static std::once_flag once;
-  std::call_once(once, [] {
-    std::memset(lut, 0, sizeof(lut));
-    lut[(int)'A'] = lut[(int)'C'] = lut[(int)'G'] = lut[(int)'T'] = lut[(int)'N'] = 1;
-  });
-  return lut;
-}
 
 // Pass 2: copy reads / quals / haplotypes into the pinned staging buffer in device layout.
 int Engine::pack_chunk(Slot& s, const Input& in) { return pack_chunk_static(s, in); }
@@ -855,7 +894,6 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
     rbase[kQueueGenericF64] = acc;
   }
   std::vector<uint32_t> fill(kMaxF64Classes, 0);
-  const uint8_t* valid = hap_valid_lut();
   size_t rpos = 0, hpos = 0, ridx = 0, hidx = 0, opos = 0;
   for (size_t k = 0; k < P.regions.size(); ++k) {
     const int64_t g = P.regions[k];
@@ -869,9 +907,6 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
       const uint32_t lp = round_up16((uint32_t)h.len);
       std::memcpy(dst, h.b, (size_t)h.len);
       std::memset(dst + h.len, 'N', lp - (uint32_t)h.len);
-      uint8_t ok = 1;
-      for (int32_t x = 0; x < h.len; ++x) ok &= valid[dst[x]];  // the copy, not the source: the caller's memory may be shared (daemon segment)
-      if (!ok) return set_error(FCS_PHMM_EINVAL, "haplotype contains a byte outside ACGTN");
       hmeta[hidx].data_off16 = (uint32_t)(hpos / 16);
       hmeta[hidx].len = (uint32_t)h.len;
       hpos += lp;
@@ -945,6 +980,7 @@ void Engine::fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) 
   p.hs_cap = 0;
   p.hap_stage_bytes = 0;
   p.n_sym = P.n_sym;
+  p.extra_bytes = P.extra_bytes;
   p.c_xx_f = 0.f; p.c_gm_f = 0.f; p.c_xx_d = 0.0; p.c_gm_d = 0.0;
   p.c_mm_f = 0.f; p.c_mx_f = 0.f;
 }

@@ -99,7 +99,8 @@ struct ChunkPlan {
   std::vector<F64Range> f64;
   std::vector<F64Queue> queues;
   bool force_double = false;
-  uint32_t n_sym = 6;         // prior-table symbol rows (5 when no haplotype of the chunk contains an N)
+  uint32_t n_sym = 6;         // prior-table symbol rows: 5 (no N in any haplotype), 6 (N), 7 + e (haplotype bytes outside ACGTN)
+  uint64_t extra_bytes = 0;   // byte e = haplotype byte value that owns symbol row kCodeExtra0 + e (it also occurs in some read)
   bool latency_mode = false;  // under-filled chunk: widest lane groups, one haplotype per task
   int f64_gcp = -1;  // >= 0: every read of the chunk shares this gap-continuation quality
   int launches() const;

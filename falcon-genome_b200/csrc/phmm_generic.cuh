@@ -27,12 +27,16 @@ struct GenericCfg {
   static constexpr int HSCALE = 32 * STRIDE / 16;
 };
 
+// dynamic shared memory of the striped kernel: the prior table (the N row is always present here)
+template <typename T>
+inline size_t generic_smem_bytes(uint32_t n_sym) { return (size_t)(n_sym < (uint32_t)kTabRows ? (uint32_t)kTabRows : n_sym) * 32u * GenericCfg<T>::STRIDE; }
+
 template <typename T, bool FROM_QUEUE>
 __global__ void __launch_bounds__(32, 8) phmm_generic(const __grid_constant__ KParams p) {
   using C = GenericCfg<T>;
   using A = Ar<T>;
   constexpr int R = C::R;
-  __shared__ __align__(128) uint8_t tab[kTabRows * 32 * C::STRIDE];
+  extern __shared__ __align__(128) uint8_t tab[];  // n_sym symbol rows of 32 * STRIDE bytes (generic_smem_bytes)
   __shared__ T lut[128];
   const int lane = threadIdx.x;
   uint8_t* tab_lane = tab + lane * C::STRIDE;
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(32, 8) phmm_generic(const __grid_constant__ KP
     for (int s = 0; s < P; ++s) {
       __syncwarp();
       tile.build(rs, (uint32_t)Lr, lane, lut, mm, tab_lane, true, s * C::ROWS, npad);
+      if (p.n_sym > (uint32_t)kCodeOther) Tile<T, 32, R, false>::build_other_rows(rs, (uint32_t)Lr, lane, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last, s * C::ROWS, npad);
       __syncwarp();
       State st;
       tile.init(st, y_init);
@@ -78,10 +83,7 @@ __global__ void __launch_bounds__(32, 8) phmm_generic(const __grid_constant__ KP
         if ((t & 31) == 0) {
           const int col = t + lane;
           int c = kCodePad;
-          if (col < Lh) {
-            c = base_code(hap[col]);
-            c = (c > kCodeN) ? kCodePad : c;
-          }
+          if (col < Lh) c = hap_code(hap[col], p.n_sym, p.extra_bytes);
           symbuf = (uint32_t)(c * C::HSCALE);
           if (has_top) {
             bM = col < Lh ? bndM[col] : T(0);

@@ -112,6 +112,20 @@ __device__ __forceinline__ int base_code(uint32_t b) {
   return c;
 }
 
+// Haplotype byte -> symbol row.  ACGT, N, then (only in launches whose haplotypes hold such bytes: n_sym > 6)
+// the byte's own row if some read of the chunk contains the same byte, else the shared OTHER row.
+__device__ __forceinline__ int hap_code(uint32_t b, uint32_t n_sym, uint64_t extra) {
+  int c = base_code(b);
+  if (c > kCodeN) {
+    c = kCodeOther;
+    for (uint32_t e = 0; e + (uint32_t)kCodeExtra0 < n_sym; ++e)
+      if (b == (uint32_t)((extra >> (8u * e)) & 0xffu)) c = kCodeExtra0 + (int)e;
+  }
+  // the host sized the table from the caller's bytes before it copied them; if the caller's memory changed in
+  // between (a shared daemon segment), stay inside the table instead of trusting the copy
+  return (uint32_t)c < n_sym ? c : kCodePad;
+}
+
 // ----------------------------------------------------------------------------------------
 // shared-memory layout of one CTA
 //   [mbarrier 128 B][prior table: n_sym x 32 lanes x STRIDE][union][raw haplotype staging]
@@ -264,6 +278,33 @@ struct Tile {
       }
       *reinterpret_cast<T*>(tab_lane + kCodePad * (32 * STRIDE) + koff) = T(0);
       if (with_n) *reinterpret_cast<T*>(tab_lane + kCodeN * (32 * STRIDE) + koff) = (pos >= 0) ? pm : T(0);
+    }
+  }
+
+  // Symbol rows beyond N (launches whose haplotypes contain bytes outside ACGTN; rare): raw-byte equality as
+  // GKL compares -- the OTHER row matches a read N only, row kCodeExtra0 + e a read N or the byte extra[e].
+  // A plain loop kept apart from build() so that the common path pays nothing for it.
+  // (static and fed by value: a non-inlined member would take the tile's address and push its arrays to local memory)
+  static __device__ __noinline__ void build_other_rows(const uint8_t* rs, uint32_t len, int lig, const T* lut, uint8_t* tab_lane, uint32_t n_sym,
+                                                       uint64_t extra, int off_last, int row0 = 0, int npad_override = -1) {
+    const uint32_t Lp = round_up16(len);
+    const int npad = (npad_override >= 0 ? npad_override : G * R - (int)len) - row0;
+    for (int k = 0; k < R; ++k) {
+      const int pos = lig * R + k - npad;
+      T pm = T(0), px = T(0);
+      uint32_t b = 0x100u;
+      if (pos >= 0) {
+        b = rs[pos];
+        const T e = lut[rs[Lp + pos] & 127u];
+        pm = A::sub(T(1), e);
+        px = A::div(e, T(3));
+      }
+      const int v = k / VW;
+      const int koff = ((ROT && v == NV - 1) ? off_last : v * 16) + (k % VW) * (int)sizeof(T);
+      for (uint32_t sym = (uint32_t)kCodeOther; sym < n_sym; ++sym) {
+        const bool m = b == (uint32_t)'N' || (sym >= (uint32_t)kCodeExtra0 && b == (uint32_t)((extra >> (8u * (sym - kCodeExtra0))) & 0xffu));
+        *reinterpret_cast<T*>(tab_lane + sym * (32 * STRIDE) + koff) = (pos >= 0) ? (m ? pm : px) : T(0);
+      }
     }
   }
 
@@ -421,6 +462,8 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   if constexpr (UA) tile.build(p.reads + (size_t)rm.data_off16 * 16u, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
   mbar_wait(bar, 0u);
   if constexpr (!UA) tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+  if (p.n_sym > (uint32_t)kCodeOther)
+    Tile<T, G, R, FORM>::build_other_rows(UA ? p.reads + (size_t)rm.data_off16 * 16u : rstage, rlen, lig, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last);
   __syncwarp();  // every lane is done with the LUT and the read staging before the stream overwrites them
   // ---- haplotype stream: [G-1 PAD] hap0 [G-1 PAD] hap1 ... [G-1 PAD]
   uint32_t off = 0;
@@ -429,8 +472,7 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
     const uint8_t* src = hstage + (hm.data_off16 - h_first.data_off16) * 16u;
     if (lane < G - 1) hs[off + lane] = (uint16_t)(kCodePad * L::HSCALE);
     for (uint32_t x = lane; x < hm.len; x += 32) {
-      int c = base_code(src[x]);
-      c = (c > kCodeN) ? kCodePad : c;  // host rejects such haplotypes; never reached
+      const int c = hap_code(src[x], p.n_sym, p.extra_bytes);
       hs[off + (G - 1) + x] = (uint16_t)(c * L::HSCALE);
     }
     off += (G - 1) + hm.len;
@@ -504,14 +546,14 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
     mbar_wait(bar, parity);
     parity ^= 1u;
     tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+    if (p.n_sym > (uint32_t)kCodeOther) Tile<T, G, R, FORM>::build_other_rows(rstage, rlen, lig, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last);
     __syncwarp();  // done with the LUT and the read staging before the stream overwrites them
     const uint32_t Lmax = __reduce_max_sync(0xffffffffu, Lh);
     const uint32_t total = Lmax + 2u * (G - 1);
     for (uint32_t x = lig; x < total; x += G) {
       int c = kCodePad;
       if (x >= (uint32_t)(G - 1) && x < (uint32_t)(G - 1) + Lh) {
-        c = base_code(hstage[x - (G - 1)]);
-        c = (c > kCodeN) ? kCodePad : c;
+        c = hap_code(hstage[x - (G - 1)], p.n_sym, p.extra_bytes);
       }
       hs[x] = (uint16_t)(c * L::HSCALE);
     }

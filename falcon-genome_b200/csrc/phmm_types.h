@@ -24,6 +24,14 @@ namespace fcsphmm {
 constexpr int kTabRows = 6;  // haplotype symbol classes: A C G T PAD N  (N last: its table row is
 constexpr int kCodePad = 4;  //   allocated only when some haplotype of the launch contains an N)
 constexpr int kCodeN = 5;
+// Haplotype bytes outside ACGTN (IUPAC codes in b37/hg19 derived haplotypes, lower case, ...).  GKL compares
+// raw bytes, so such a byte matches a read base only if the read holds the very same byte or an N.  Bytes
+// that no read of the chunk contains share the OTHER row (matches a read N only); the few that do occur in
+// reads as well get a row of their own (kCodeExtra0 + e, byte values in KParams::extra_bytes).
+constexpr int kCodeOther = 6;
+constexpr int kCodeExtra0 = 7;
+constexpr int kMaxExtraSyms = 8;
+constexpr int kMaxSyms = kCodeExtra0 + kMaxExtraSyms;
 constexpr int kMaxF64Classes = 40;
 constexpr int kQueueGenericF64 = kMaxF64Classes - 1;  // FP64 rerun queue of the striped generic path
 
@@ -81,7 +89,8 @@ struct KParams {
   uint32_t seg_max[32];
   uint32_t hs_cap;         // u16 entries of haplotype stream in shared memory
   uint32_t hap_stage_bytes;  // bytes of raw haplotype staging in shared memory
-  uint32_t n_sym;            // prior-table symbol rows in shared memory: 5 (no N in any haplotype) or 6
+  uint32_t n_sym;            // prior-table symbol rows in shared memory: 5 (no N in any haplotype), 6 (N), 7 + e (non-ACGTN bytes)
+  uint64_t extra_bytes;      // byte e = value of the haplotype byte that owns symbol row kCodeExtra0 + e
   // generic (striped) path: host-built pair list for the FP32 pass, per-CTA boundary scratch rows
   const RerunEntry* gen_list;
   uint32_t gen_count;

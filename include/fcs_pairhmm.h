@@ -50,11 +50,11 @@ extern "C" {
 
 /* error codes (0 = ok, negative = failure; fcs_pairhmm_last_error() has the text) */
 #define FCS_PHMM_OK 0
-#define FCS_PHMM_EINVAL (-1)       /* bad argument: null pointer, non-positive length, haplotype byte outside ACGTN */
+#define FCS_PHMM_EINVAL (-1)       /* bad argument: null pointer, non-positive length */
 #define FCS_PHMM_ENODEV (-2)       /* no usable CUDA device (no CPU fallback exists) */
 #define FCS_PHMM_ECUDA (-3)        /* a CUDA runtime call or kernel failed */
 #define FCS_PHMM_ENOMEM (-4)       /* host or device allocation failed */
-#define FCS_PHMM_EUNSUPPORTED (-5) /* shape outside what the kernels cover (see FCS_PHMM_MAX_READ_LEN) */
+#define FCS_PHMM_EUNSUPPORTED (-5) /* shape outside what the kernels cover (FCS_PHMM_MAX_READ_LEN; > 8 distinct non-ACGTN byte values shared by reads and haplotypes of a chunk) */
 #define FCS_PHMM_ETICKET (-6)      /* unknown or already-waited ticket */
 
 #define FCS_PHMM_MAX_READ_LEN 65535

@@ -8,6 +8,10 @@
  * VectorLoglessPairHMM does: initNative once, computeLikelihoodsNative per region, doneNative at the end.
  * Like a copying JVM it hands out COPIES from Get<Type>ArrayElements and only writes a double array back
  * on Release with mode 0, so the test also sees whether the shim releases what it pins and commits the output.
+ * Local references are counted: every object the "VM" returns (array elements, fields, classes) is one live
+ * reference until DeleteLocalRef; a native frame is only guaranteed 16 (more after EnsureLocalCapacity), and the
+ * test reads back the high-water mark.  Modes: 1 = the holder classes lack the expected fields (GetFieldID leaves
+ * NoSuchFieldError pending), 2 = computeLikelihoodsNative is called although initNative was never called.
  *
  * It is not a JVM and proves nothing about ABI compatibility with one; it checks the shim's logic.
  */
@@ -33,10 +37,23 @@ static struct _jfieldID g_fid[5] = {{0}, {1}, {2}, {3}, {4}};
 static int g_pinned;           /* Get*ArrayElements minus Release*ArrayElements */
 static int g_bad_release;      /* releases of pointers that were never handed out, or byte releases that would copy back */
 static char g_exception[512];  /* pending exception: "<class>: <message>" */
+static int g_live_refs, g_max_live_refs, g_ref_capacity = 16;
+static int g_calls_with_pending; /* JNI calls that are illegal while an exception is pending */
+static int g_break_fields;
+static jobject new_ref(jobject o) {
+  if (o && ++g_live_refs > g_max_live_refs) g_max_live_refs = g_live_refs;
+  return o;
+}
+#define PENDING_GUARD() do { if (g_exception[0]) ++g_calls_with_pending; } while (0)
 
 static jfieldID f_GetFieldID(JNIEnv* env, jclass cls, const char* name, const char* sig) {
   (void)env;
+  PENDING_GUARD();
   static const char* read_fields[5] = {"readBases", "readQuals", "insertionGOP", "deletionGOP", "overallGCP"};
+  if (g_break_fields && strcmp(name, "insertionGOP") == 0) {
+    snprintf(g_exception, sizeof(g_exception), "java/lang/NoSuchFieldError: %s", name);
+    return NULL;
+  }
   if (!cls || cls->kind != K_CLASS || strcmp(sig, "[B") != 0) return NULL;
   if (strcmp(cls->name, "ReadDataHolder") == 0) {
     for (int i = 0; i < 5; ++i)
@@ -48,7 +65,8 @@ static jfieldID f_GetFieldID(JNIEnv* env, jclass cls, const char* name, const ch
 }
 static jobject f_GetObjectField(JNIEnv* env, jobject o, jfieldID f) {
   (void)env;
-  return (o && f && o->kind == K_HOLDER) ? o->field[f->idx] : NULL;
+  PENDING_GUARD();
+  return new_ref((o && f && o->kind == K_HOLDER) ? o->field[f->idx] : NULL);
 }
 static jsize f_GetArrayLength(JNIEnv* env, jarray a) {
   (void)env;
@@ -56,7 +74,8 @@ static jsize f_GetArrayLength(JNIEnv* env, jarray a) {
 }
 static jobject f_GetObjectArrayElement(JNIEnv* env, jobjectArray a, jsize i) {
   (void)env;
-  return (a && a->kind == K_OBJECTS && i >= 0 && i < a->len) ? ((jobject*)a->data)[i] : NULL;
+  PENDING_GUARD();
+  return new_ref((a && a->kind == K_OBJECTS && i >= 0 && i < a->len) ? ((jobject*)a->data)[i] : NULL);
 }
 static jbyte* f_GetByteArrayElements(JNIEnv* env, jbyteArray a, jboolean* is_copy) {
   (void)env;
@@ -93,18 +112,52 @@ static void f_ReleaseDoubleArrayElements(JNIEnv* env, jdoubleArray a, jdouble* p
 static struct _jobject g_exc_class = {K_CLASS, 0, NULL, {0}, NULL};
 static jclass f_FindClass(JNIEnv* env, const char* name) {
   (void)env;
+  PENDING_GUARD();
   g_exc_class.name = name;
-  return &g_exc_class;
+  return new_ref(&g_exc_class);
 }
 static jint f_ThrowNew(JNIEnv* env, jclass cls, const char* msg) {
   (void)env;
+  PENDING_GUARD();
   snprintf(g_exception, sizeof(g_exception), "%s: %s", cls && cls->name ? cls->name : "?", msg ? msg : "");
   return 0;
+}
+static jboolean f_ExceptionCheck(JNIEnv* env) {
+  (void)env;
+  return g_exception[0] != 0;
+}
+static void f_DeleteLocalRef(JNIEnv* env, jobject o) {
+  (void)env;
+  if (o) --g_live_refs;
+}
+static jint f_EnsureLocalCapacity(JNIEnv* env, jint n) {
+  (void)env;
+  if (n > g_ref_capacity) g_ref_capacity = n;
+  return 0;
+}
+static void f_GetByteArrayRegion(JNIEnv* env, jbyteArray a, jsize start, jsize len, jbyte* buf) {
+  (void)env;
+  PENDING_GUARD();
+  if (!a || a->kind != K_BYTES || start < 0 || len < 0 || start + len > a->len) {
+    snprintf(g_exception, sizeof(g_exception), "java/lang/ArrayIndexOutOfBoundsException: GetByteArrayRegion");
+    return;
+  }
+  memcpy(buf, (const jbyte*)a->data + start, (size_t)len);
+}
+static void f_SetDoubleArrayRegion(JNIEnv* env, jdoubleArray a, jsize start, jsize len, const jdouble* buf) {
+  (void)env;
+  PENDING_GUARD();
+  if (!a || a->kind != K_DOUBLES || start < 0 || len < 0 || start + len > a->len) {
+    snprintf(g_exception, sizeof(g_exception), "java/lang/ArrayIndexOutOfBoundsException: SetDoubleArrayRegion");
+    return;
+  }
+  memcpy((jdouble*)a->data + start, buf, sizeof(jdouble) * (size_t)len);
 }
 
 static const struct JNINativeInterface_ g_table = {
     f_GetFieldID,          f_GetObjectField,          f_GetArrayLength,           f_GetObjectArrayElement, f_GetByteArrayElements,
-    f_ReleaseByteArrayElements, f_GetDoubleArrayElements, f_ReleaseDoubleArrayElements, f_FindClass,             f_ThrowNew};
+    f_ReleaseByteArrayElements, f_GetDoubleArrayElements, f_ReleaseDoubleArrayElements, f_FindClass,             f_ThrowNew,
+    f_ExceptionCheck,      f_DeleteLocalRef,          f_EnsureLocalCapacity,      f_GetByteArrayRegion,    f_SetDoubleArrayRegion};
 
 typedef void (*init_fn)(JNIEnv*, jclass, jclass, jclass, jboolean, jint);
 typedef void (*compute_fn)(JNIEnv*, jobject, jobjectArray, jobjectArray, jdoubleArray);
@@ -124,6 +177,12 @@ static void free_obj(jobject o) {
   free(o);
 }
 
+/* test knobs / read-backs */
+__attribute__((visibility("default"))) void fake_jvm_set_mode(int break_fields) { g_break_fields = break_fields; }
+__attribute__((visibility("default"))) int fake_jvm_max_live_refs(void) { return g_max_live_refs; }
+__attribute__((visibility("default"))) int fake_jvm_ref_capacity(void) { return g_ref_capacity; }
+__attribute__((visibility("default"))) int fake_jvm_calls_with_pending_exception(void) { return g_calls_with_pending; }
+
 /*
  * Runs one session against the shim at `shim_path`: initNative, `repeats` x computeLikelihoodsNative on the
  * region given as concatenated planes (read r = rd_len[r] bytes at rd_off[r] of each plane; hap h likewise),
@@ -136,6 +195,8 @@ __attribute__((visibility("default"))) int fake_jvm_run(const char* shim_path, c
                                                         const int32_t* hp_len, int32_t n_haps, int32_t use_double, int32_t max_threads,
                                                         int32_t repeats, double* out, char* err, int32_t err_cap) {
   g_pinned = g_bad_release = 0;
+  g_live_refs = g_max_live_refs = g_calls_with_pending = 0;
+  g_ref_capacity = 16;
   g_exception[0] = 0;
   if (err_cap > 0) err[0] = 0;
   void* so = dlopen(shim_path, RTLD_NOW | RTLD_LOCAL);
@@ -156,7 +217,8 @@ __attribute__((visibility("default"))) int fake_jvm_run(const char* shim_path, c
   struct _jobject read_cls = {K_CLASS, 0, NULL, {0}, "ReadDataHolder"}, hap_cls = {K_CLASS, 0, NULL, {0}, "HaplotypeDataHolder"};
   struct _jobject self = {K_HOLDER, 0, NULL, {0}, NULL};
   int rc = 0;
-  init(env, &read_cls, &read_cls, &hap_cls, (jboolean)(use_double != 0), max_threads);
+  const int skip_init = max_threads < 0; /* test mode: computeLikelihoodsNative without a successful initNative */
+  if (!skip_init) init(env, &read_cls, &read_cls, &hap_cls, (jboolean)(use_double != 0), max_threads);
   if (g_exception[0]) {
     snprintf(err, (size_t)err_cap, "%s", g_exception);
     dlclose(so);
@@ -190,6 +252,12 @@ __attribute__((visibility("default"))) int fake_jvm_run(const char* shim_path, c
     rc = -1;
   } else if (g_pinned != 0 || g_bad_release != 0) {
     snprintf(err, (size_t)err_cap, "array elements not released properly: %d still pinned, %d bad releases", g_pinned, g_bad_release);
+    rc = -1;
+  } else if (g_live_refs != 0 || g_max_live_refs > g_ref_capacity) {
+    snprintf(err, (size_t)err_cap, "local references: %d leaked, high-water mark %d of a capacity of %d", g_live_refs, g_max_live_refs, g_ref_capacity);
+    rc = -1;
+  } else if (g_calls_with_pending) {
+    snprintf(err, (size_t)err_cap, "%d JNI calls were made while an exception was pending", g_calls_with_pending);
     rc = -1;
   }
   for (int32_t r = 0; r < n_reads; ++r) {

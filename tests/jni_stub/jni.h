@@ -35,5 +35,10 @@ struct JNINativeInterface_ {
   void (*ReleaseDoubleArrayElements)(JNIEnv*, jdoubleArray, jdouble*, jint);
   jclass (*FindClass)(JNIEnv*, const char*);
   jint (*ThrowNew)(JNIEnv*, jclass, const char*);
+  jboolean (*ExceptionCheck)(JNIEnv*);
+  void (*DeleteLocalRef)(JNIEnv*, jobject);
+  jint (*EnsureLocalCapacity)(JNIEnv*, jint);
+  void (*GetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, jbyte*);
+  void (*SetDoubleArrayRegion)(JNIEnv*, jdoubleArray, jsize, jsize, const jdouble*);
 };
 #endif

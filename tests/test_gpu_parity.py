@@ -284,15 +284,77 @@ def test_errors(hmm):
 
     rd = (b"ACGT", bytes([30] * 4), bytes([45] * 4), bytes([45] * 4), bytes([10] * 4))
     with pytest.raises(PairHMMError) as e:
-        hmm.compute_likelihoods([rd], [b"ACXT"])
-    assert e.value.code == -1
-    with pytest.raises(PairHMMError) as e:
         hmm.compute_likelihoods([rd], [b""])
     assert e.value.code == -1
     # empty regions are fine
     b = FlatBatch.from_regions([Region([], [b"ACGT"]), Region([rd], []), Region([rd], [b"ACGT"])])
     out, used = hmm.compute_flat(b)
     assert out.shape == (1,) and np.isfinite(out[0])
+
+
+def test_haplotype_bytes_outside_acgtn(hmm, oracle):
+    """GKL compares raw bytes, so a haplotype may hold IUPAC codes, lower case or anything else (b37 / hg19
+    carry such bases): the byte matches a read base only if the read holds the very same byte or an N.  The
+    library must score such input like the oracle's raw-byte rule instead of refusing it -- single-pass
+    kernels of every form, FP64 reruns and the striped path; bytes that occur on both sides get their own
+    symbol rows (up to 8), the others share one."""
+    from falcon_genome_b200 import PairHMMError
+
+    rng = np.random.default_rng(606)
+
+    def seq(n, alpha=b"ACGT"):
+        return bytes(rng.choice(list(alpha), n).astype(np.uint8))
+
+    def spoil(h, alpha, rate):
+        h = bytearray(h)
+        for k in np.nonzero(rng.random(len(h)) < rate)[0]:
+            h[k] = int(rng.choice(list(alpha)))
+        return bytes(h)
+
+    regs = []
+    # (a) haplotype-only foreign bytes (the realistic case): IUPAC + lower case + N, reads clean / with N
+    h0 = seq(320)
+    haps = [h0, spoil(h0, b"RYKMSWnacgt", 0.03), spoil(h0[20:300], b"NRY", 0.05), spoil(h0[:150], b"*-.", 0.02)]
+    regs.append(Region(_uniform_indel_region(rng, 150, 16, h0, n_rate=0.01), haps))          # all-uniform kernels
+    regs.append(Region(_uniform_indel_region(rng, 101, 9, h0, 40, 38, 10), haps))            # uniform-GCP kernels
+    # (b) the same foreign bytes in reads and haplotypes: equal bytes match (raw compare), different ones do not
+    reads = []
+    for _ in range(12):
+        L = int(rng.integers(30, 260))
+        s0 = int(rng.integers(0, 320 - 30))
+        b = bytearray((haps[1] * 2)[s0:s0 + L])
+        for k in rng.integers(0, L, max(1, L // 15)):
+            b[k] = int(rng.choice(list(b"ACGTNRYKa")))
+        reads.append((bytes(b), bytes(rng.integers(2, 42, L).astype(np.uint8)), bytes(rng.integers(10, 50, L).astype(np.uint8)),
+                      bytes(rng.integers(10, 50, L).astype(np.uint8)), bytes(rng.integers(5, 30, L).astype(np.uint8))))
+    regs.append(Region(reads, haps))                                                          # general form
+    # (c) low qualities + unrelated foreign-byte haplotype: FP64 reruns see the same table
+    lowq = [(seq(250), bytes(rng.integers(2, 8, 250).astype(np.uint8)), bytes([12] * 250), bytes([12] * 250), bytes([10] * 250)) for _ in range(6)]
+    regs.append(Region(lowq, [spoil(seq(900), b"RYN", 0.05), spoil(seq(700), b"MK", 0.02)]))
+    # (d) striped path: long read and long haplotype with foreign bytes on both sides
+    hl = spoil(seq(2400), b"RYNn", 0.02)
+    rl = bytearray(hl[100:700]); rl[17] = ord("R"); rl[300] = ord("y"); rl[301] = ord("N")
+    regs.append(Region([(bytes(rl), bytes([25] * 600), bytes([40] * 600), bytes([40] * 600), bytes([10] * 600)),
+                        (hl[5:155], bytes([30] * 150), bytes([45] * 150), bytes([45] * 150), bytes([10] * 150))], [hl, hl[50:2100]]))
+    b = FlatBatch.from_regions(regs)
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+    assert used.any() and not used.all()
+    # region by region (other chunk alphabets: a region alone may need fewer symbol rows) -> same bits
+    for g in range(b.n_regions):
+        bg = b.select([g])
+        og, ug = hmm.compute_flat(bg)
+        o0 = int(b.reg_out0[g])
+        assert np.array_equal(og, out[o0:o0 + len(og)]) and np.array_equal(ug, used[o0:o0 + len(og)])
+    # a known answer: 'R' in the haplotype matches a read 'R' and a read 'N', nothing else
+    rd = lambda s: (s, bytes([30]), bytes([45]), bytes([45]), bytes([10]))  # noqa: E731
+    m = np.array([hmm.compute_likelihoods([rd(x)], [b"R"])[0, 0] for x in (b"R", b"N", b"A", b"Y")])
+    assert np.allclose(m[:2], np.log10(0.999 * 0.9), atol=5e-6) and np.allclose(m[2:], np.log10(0.001 / 3 * 0.9), atol=5e-6)
+    # more than 8 distinct foreign byte values shared by reads and haplotypes of one chunk: refused, not mis-scored
+    many = bytes(range(ord("a"), ord("a") + 12))
+    with pytest.raises(PairHMMError) as e:
+        hmm.compute_likelihoods([(many, bytes([30] * 12), bytes([45] * 12), bytes([45] * 12), bytes([10] * 12))], [many])
+    assert e.value.code == -5
 
 
 def test_full_size_config2_properties(hmm):
@@ -365,7 +427,8 @@ def test_fuzz_random_shapes_and_bytes(hmm, oracle, seed):
     regs = []
     for _ in range(40):
         nh = int(rng.integers(1, 6))
-        haps = [bytes(rng.choice(list(b"ACGTN"), int(rng.integers(1, 700)), p=[.24, .24, .24, .24, .04]).astype(np.uint8)) for _ in range(nh)]
+        alpha, pr = (b"ACGTN", [.24, .24, .24, .24, .04]) if rng.random() < 0.7 else (b"ACGTNRYa", [.23, .23, .23, .23, .04, .02, .01, .01])
+        haps = [bytes(rng.choice(list(alpha), int(rng.integers(1, 700)), p=pr).astype(np.uint8)) for _ in range(nh)]
         reads = []
         for _r in range(int(rng.integers(1, 12))):
             L = int(rng.choice([rng.integers(1, 30), rng.integers(30, 200), rng.integers(200, 420)]))

@@ -47,6 +47,11 @@ class PrepParams(C.Structure):
                 ("pcr_model", C.c_int32)]
 
 
+class FinalizeParams(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("reserved", C.c_int32), ("log10_global_mismapping_rate", C.c_double),
+                ("expected_error_rate_per_base", C.c_double)]
+
+
 class PlanInfo(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_tasks", C.c_int64), ("n_generic_pairs", C.c_int64), ("in_bytes", C.c_int64),
                 ("max_smem_bytes", C.c_int64), ("n_launches_f32", C.c_int32), ("n_launches_f64", C.c_int32), ("n_sym", C.c_int32),
@@ -95,6 +100,8 @@ SIGNATURES = {
     "fcs_pairhmm_capture_free": (None, [C.c_void_p]),
     "fcs_pairhmm_prepare_read": (C.c_int, [u8p, u8p, C.c_int32, C.c_int32, u8p, u8p, C.POINTER(PrepParams), u8p, u8p, u8p, u8p]),
     "fcs_pairhmm_finalize_region": (C.c_int, [f64p, C.c_int32, C.c_int32, i32p, C.c_double, C.c_double, u8p]),
+    "fcs_pairhmm_set_finalize": (C.c_int, [C.c_void_p, C.POINTER(FinalizeParams)]),
+    "fcs_pairhmm_compute_flat_finalized": (C.c_int, [C.c_void_p, C.POINTER(FlatStruct), f64p, u8p, u8p]),
     "fcs_pairhmm_plan_check": (C.c_int, [C.POINTER(FlatStruct), C.c_int32, C.POINTER(PlanInfo)]),
     "fcs_pairhmm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "fcs_pairhmm_reset_stats": (C.c_int, [C.c_void_p]),

@@ -143,6 +143,25 @@ int fcs_pairhmm_compute_flat(fcs_phmm_handle* h, const fcs_phmm_flat_batch* b, d
   API_CATCH
 }
 
+int fcs_pairhmm_set_finalize(fcs_phmm_handle* h, const fcs_phmm_finalize_params* p) {
+  if (!h) return set_error(FCS_PHMM_EINVAL, "null handle");
+  if (p && p->enabled && !(p->log10_global_mismapping_rate <= 0.0) ) return set_error(FCS_PHMM_EINVAL, "log10 mismapping rate must be <= 0");
+  if (p && p->enabled) h->e->set_finalize(true, p->log10_global_mismapping_rate, p->expected_error_rate_per_base);
+  else h->e->set_finalize(false, -4.5, 0.02);
+  return FCS_PHMM_OK;
+}
+
+int fcs_pairhmm_compute_flat_finalized(fcs_phmm_handle* h, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64, uint8_t* poorly) {
+  if (!h) return set_error(FCS_PHMM_EINVAL, "null handle");
+  API_TRY
+  int rc = check_flat(b);
+  if (rc != FCS_PHMM_OK) return rc;
+  if (!out) return set_error(FCS_PHMM_EINVAL, "null out");
+  std::unique_ptr<Input> in = make_flat_input(*b, out, used_fp64, nullptr, poorly);
+  return h->e->compute(*in);
+  API_CATCH
+}
+
 int fcs_pairhmm_submit(fcs_phmm_handle* h, const fcs_phmm_region* regions, int32_t n_regions, fcs_phmm_ticket* ticket) {
   if (!h) return set_error(FCS_PHMM_EINVAL, "null handle");
   if (!ticket) return set_error(FCS_PHMM_EINVAL, "null ticket");

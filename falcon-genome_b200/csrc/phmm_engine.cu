@@ -83,6 +83,10 @@ static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid
 // Runs over every read of every call (up to three planes): 16 bytes per step, early exit.
 static int uniform_gcp(const uint8_t* c, int32_t len) {
   const uint8_t v = c[0] & 127u;
+  // fast path: all bytes equal <=> c[0..len-1) == c[1..len); libc's memcmp is dispatched to the widest vectors of the
+  // host and stops at the first difference.  Bytes with the top bit set (masked by the kernels) take the loop below.
+  if (len > 1 && std::memcmp(c, c + 1, (size_t)len - 1) == 0) return (int)v;
+  if (len == 1) return (int)v;
   int32_t i = 0;
 #if defined(__SSE2__)
   const __m128i vv = _mm_set1_epi8((char)v), m7 = _mm_set1_epi8(0x7f);
@@ -101,6 +105,49 @@ static int uniform_gcp(const uint8_t* c, int32_t len) {
   for (; i < len; ++i)
     if ((c[i] & 127u) != v) return -1;
   return (int)v;
+}
+
+// dst[0, round_up16(len)) = src[0, len) followed by `pad` bytes.  The packer runs this ten times per read on
+// 100-250 byte pieces: 16-byte loads/stores inline instead of a memcpy + memset call pair each.  Never reads
+// past src + len (the caller's arrays may end there).
+static inline void copy_padded16(uint8_t* dst, const uint8_t* src, uint32_t len, uint8_t pad) {
+#if defined(__SSE2__)
+  uint32_t i = 0;
+  for (; i + 16 <= len; i += 16) _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
+  if (i < len) {
+    // last, partly filled block: the padding first, then the final 16 source bytes on top of it (they overlap the
+    // previous block with identical data) -- no byte loop, no read or write outside [0, len) / [0, round_up16(len))
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm_set1_epi8((char)pad));
+    if (len >= 16) _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + len - 16), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + len - 16)));
+    else for (uint32_t k = 0; k < len; ++k) dst[k] = src[k];
+  }
+#else
+  std::memcpy(dst, src, len);
+  std::memset(dst + len, pad, round_up16(len) - len);
+#endif
+}
+
+// Which byte classes a haplotype holds: bit 0 = an N, bit 1 = a byte outside ACGTN.
+static inline uint32_t hap_classes(const uint8_t* b, int32_t len) {
+  uint32_t seen = 0;
+  int32_t i = 0;
+#if defined(__SSE2__)
+  const __m128i vA = _mm_set1_epi8('A'), vC = _mm_set1_epi8('C'), vG = _mm_set1_epi8('G'), vT = _mm_set1_epi8('T'), vN = _mm_set1_epi8('N');
+  for (; i + 16 <= len; i += 16) {
+    const __m128i w = _mm_loadu_si128(reinterpret_cast<const __m128i*>(b + i));
+    const __m128i acgt = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(w, vA), _mm_cmpeq_epi8(w, vC)), _mm_or_si128(_mm_cmpeq_epi8(w, vG), _mm_cmpeq_epi8(w, vT)));
+    const int mn = _mm_movemask_epi8(_mm_cmpeq_epi8(w, vN));
+    const int ma = _mm_movemask_epi8(acgt);
+    if (mn) seen |= 1u;
+    if ((ma | mn) != 0xffff) seen |= 2u;
+  }
+#endif
+  for (; i < len; ++i) {
+    const uint8_t c = b[i];
+    if (c == 'N') seen |= 1u;
+    else if (c != 'A' && c != 'C' && c != 'G' && c != 'T') seen |= 2u;
+  }
+  return seen;
 }
 
 static cudaError_t init_slot(Slot& s);
@@ -363,6 +410,12 @@ int Engine::ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t de
   return FCS_PHMM_OK;
 }
 
+// developer knob: FCS_PHMM_NO_TWO_PLANE=1 packs all five planes of every read
+static bool two_plane_enabled() {
+  static const bool on = env_i64("FCS_PHMM_NO_TWO_PLANE", 0) == 0;
+  return on;
+}
+
 // haplotype byte classes: 0 = ACGT, bit 0 = N, bit 1 = any other byte
 static const uint8_t* hap_byte_class() {
   static uint8_t lut[256];
@@ -380,6 +433,16 @@ static const uint8_t* hap_byte_class() {
 // (read group x haplotype run) tasks per kernel class and size every section.
 namespace {
 
+// developer probe (FCS_PHMM_PLAN_PROF=1): where the planner's time goes, summed per thread and printed by plan_check
+struct PlanProf { double scan = 0, region = 0, sort = 0, tasks = 0, f64 = 0, post = 0; };
+static thread_local PlanProf t_prof;
+static const bool g_plan_prof = env_i64("FCS_PHMM_PLAN_PROF", 0) != 0;
+struct ProfScope {
+  double* acc; double t0;
+  explicit ProfScope(double* a) : acc(g_plan_prof ? a : nullptr), t0(acc ? now_ms() : 0) {}
+  ~ProfScope() { if (acc) *acc += now_ms() - t0; }
+};
+
 struct Planner {
   const Input& in;
   Slot& s;
@@ -390,6 +453,7 @@ struct Planner {
   int sm_count = 148;
   bool shape_tail = true;  // false for every chunk of a call but the last one on its device: their tails overlap the next chunk
   bool coarse_classes = true;  // unpopular read lengths round up to the coarse class grid (off for resident batches: one launch set, no chunk overlap)
+  bool finalize = false;       // reserve the sections of the per-read cap / poorly-modelled epilogue
   std::vector<uint8_t> fine_len;  // per read length: bit `form` set = keep the exact class (bit 0 also covers the uniform-GCP form)
 
   int run(const std::vector<int64_t>& regions, size_t first, size_t& next) {
@@ -398,6 +462,7 @@ struct Planner {
     P.force_double = force_double;
     for (auto& b : s.buckets) { b.tasks.clear(); b.hs = 0; b.stage = 0; b.cls_mask = 0; }
     s.order.clear();
+    s.ukeys.clear();
     s.genlist.clear();
     s.gen_flags.clear();
     uint32_t gen64_cap = 0, gen_maxlh = 0;
@@ -444,6 +509,7 @@ struct Planner {
     // closely enough for a popularity test)
     std::vector<uint32_t> len_hist(1025, 0);
     {
+      ProfScope ps(&t_prof.scan);
       uint64_t n_elig = 0, n_tot = 0;
       for (size_t kk = first; kk < regions.size(); ++kk) {
         int32_t nr = 0, nh = 0;
@@ -508,6 +574,7 @@ struct Planner {
     int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
     size_t reads_bytes = 0, haps_bytes = 0;
     std::vector<uint32_t> lens, hlens;
+    std::vector<uint64_t> sort_keys;
     size_t k = first;
     for (; k < regions.size(); ++k) {
       const int64_t g = regions[k];
@@ -526,6 +593,7 @@ struct Planner {
       hlens.resize(nh);
       uint64_t sum_r = 0, sum_h = 0;
       size_t rb = 0, hb = 0;
+      const double tp0 = g_plan_prof ? now_ms() : 0;
       for (int32_t i = 0; i < nr; ++i) {
         const InRead r = in.read(g, i);
         if (r.len <= 0 || !r.b || !r.q || !r.i || !r.d || !r.c)
@@ -535,7 +603,7 @@ struct Planner {
         gcps[i] = all_gcp[qual_off[k] + (size_t)i];
         ukeys[i] = all_ukey[qual_off[k] + (size_t)i];
         sum_r += (uint64_t)r.len;
-        rb += 5u * round_up16((uint32_t)r.len);
+        rb += read_blob_bytes((uint32_t)r.len, two_plane_enabled() && ukeys[i] >= 0);
       }
       for (int32_t j = 0; j < nh; ++j) {
         const InHap h = in.hap(g, j);
@@ -544,11 +612,10 @@ struct Planner {
         hlens[j] = (uint32_t)h.len;
         sum_h += (uint64_t)h.len;
         {
-          const uint8_t* cls = hap_byte_class();
-          uint8_t seen = 0;
-          for (int32_t x = 0; x < h.len; ++x) seen |= cls[h.b[x]];
+          const uint32_t seen = hap_classes(h.b, h.len);
           any_n = any_n || (seen & 1u);
-          if (seen & 2u) {
+          if (seen & 2u) {  // rare: collect the foreign byte values
+            const uint8_t* cls = hap_byte_class();
             any_other = true;
             for (int32_t x = 0; x < h.len; ++x)
               if (cls[h.b[x]] & 2u) hap_other[h.b[x]] = true;
@@ -563,6 +630,7 @@ struct Planner {
            reads_bytes + rb + haps_bytes + hb > (size_t)1 << 31))
         break;
       if (pairs > 0x7fffffffULL) return set_error(FCS_PHMM_EUNSUPPORTED, "region with more than 2^31 pairs");
+      const double tp1 = g_plan_prof ? now_ms() : 0;
       // ---- reads sorted by length (descending, stable) so a lane group shares a class
       const size_t ord0 = s.order.size();
       s.order.resize(ord0 + nr);
@@ -570,7 +638,15 @@ struct Planner {
       std::iota(ord, ord + nr, 0u);
       bool same = true;
       for (int32_t i = 1; i < nr && same; ++i) same = lens[i] == lens[0];
-      if (!same) std::stable_sort(ord, ord + nr, [&](uint32_t a, uint32_t b) { return lens[a] > lens[b]; });
+      if (!same) {
+        // descending length, ties in the caller's order: one packed key per read, plain sort (std::stable_sort allocates a
+        // scratch buffer per call, and this runs once per region)
+        sort_keys.resize((size_t)nr);
+        for (int32_t i = 0; i < nr; ++i) sort_keys[(size_t)i] = ((uint64_t)(0xffffffffu - lens[i]) << 32) | (uint32_t)i;
+        std::sort(sort_keys.begin(), sort_keys.end());
+        for (int32_t i = 0; i < nr; ++i) ord[i] = (uint32_t)(sort_keys[(size_t)i] & 0xffffffffu);
+      }
+      const double tp2 = g_plan_prof ? now_ms() : 0;
       // ---- tasks
       // Tail shaping (equal-size tasks finish in lock step otherwise): the reads within the last ~1.5
       // waves of the chunk are cut into tasks of half the haplotype columns, those within the last ~0.5
@@ -663,6 +739,7 @@ struct Planner {
         }
         i += cnt;
       }
+      const double tp3 = g_plan_prof ? now_ms() : 0;
       // ---- FP64 queue capacity per class (worst case: every pair of the read falls back)
       for (int32_t i = 0; i < nr; ++i) {
         if (long_hap || lens[i] > (uint32_t)kGenericMaxSinglePassRead) continue;  // counted in gen64_cap
@@ -676,6 +753,7 @@ struct Planner {
         chunk_gcp = (chunk_gcp == -2) ? gcps[i] : (chunk_gcp == gcps[i] ? chunk_gcp : -1);
       }
       hap_len_chunk.insert(hap_len_chunk.end(), hlens.begin(), hlens.end());
+      s.ukeys.insert(s.ukeys.end(), ukeys.begin(), ukeys.begin() + nr);
       P.regions.push_back(g);
       P.reg_out0.push_back(P.n_pairs);
       P.n_reads += nr;
@@ -684,8 +762,13 @@ struct Planner {
       P.cells += cells;
       reads_bytes += rb;
       haps_bytes += hb;
+      if (g_plan_prof) {
+        const double tp4 = now_ms();
+        t_prof.region += tp1 - tp0; t_prof.sort += tp2 - tp1; t_prof.tasks += tp3 - tp2; t_prof.f64 += tp4 - tp3;
+      }
     }
     next = k;
+    ProfScope ps_post(&t_prof.post);
     // ---- layout
     size_t off = 0;
     P.latency_mode = min_G != 0;
@@ -718,6 +801,9 @@ struct Planner {
     P.off_haps = off; off = align_up(off + haps_bytes, 256);
     P.off_rmeta = off; off = align_up(off + P.n_reads * sizeof(ReadMeta), 256);
     P.off_hmeta = off; off = align_up(off + P.n_haps * sizeof(HapMeta), 256);
+    P.finalize = finalize;
+    P.off_rnh = off;
+    if (finalize) off = align_up(off + P.n_reads * sizeof(uint32_t), 256);
     P.off_tasks = off;
     P.n_tasks = 0;
     for (size_t bi = 0; bi < s.buckets.size(); ++bi) {
@@ -867,6 +953,7 @@ struct Planner {
     P.off_out = off; off += P.n_pairs * sizeof(double);
     P.off_raw = off; if (keep_raw) off += P.n_pairs * sizeof(float);
     P.off_used = off; off += P.n_pairs;
+    P.off_poor = off; if (finalize) off += P.n_reads;
     P.total_bytes = align_up(off, 256);
     return FCS_PHMM_OK;
   }
@@ -905,8 +992,7 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
       const InHap h = in.hap(g, j);
       uint8_t* dst = base + P.off_haps + hpos;
       const uint32_t lp = round_up16((uint32_t)h.len);
-      std::memcpy(dst, h.b, (size_t)h.len);
-      std::memset(dst + h.len, 'N', lp - (uint32_t)h.len);
+      copy_padded16(dst, h.b, (uint32_t)h.len, (uint8_t)'N');
       hmeta[hidx].data_off16 = (uint32_t)(hpos / 16);
       hmeta[hidx].len = (uint32_t)h.len;
       hpos += lp;
@@ -919,9 +1005,16 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
       const uint32_t lp = round_up16((uint32_t)r.len);
       uint8_t* dst = base + P.off_reads + rpos;
       const uint8_t* src[5] = {r.b, r.q, r.i, r.d, r.c};
-      for (int pl = 0; pl < 5; ++pl) {
-        std::memcpy(dst + (size_t)pl * lp, src[pl], (size_t)r.len);
-        std::memset(dst + (size_t)pl * lp + r.len, 0, lp - (uint32_t)r.len);
+      // constant insertion / deletion / continuation qualities (the planner's scan): two planes + a 16-byte trailer
+      const int ukey = s.ukeys[opos + oi];
+      const bool two_plane = two_plane_enabled() && ukey >= 0;
+      for (int pl = 0; pl < (two_plane ? 2 : 5); ++pl) copy_padded16(dst + (size_t)pl * lp, src[pl], (uint32_t)r.len, 0);
+      if (two_plane) {
+        uint8_t* tr = dst + 2 * (size_t)lp;
+        std::memset(tr, 0, 16);
+        tr[0] = (uint8_t)((ukey >> 8) & 127);   // insertion
+        tr[1] = (uint8_t)((ukey >> 16) & 127);  // deletion
+        tr[2] = (uint8_t)(ukey & 127);          // gap continuation
       }
       int c64 = s.gen_flags[ridx] ? kQueueGenericF64 : qid_of_len(r.len);
       if (P.latency_mode && !s.gen_flags[ridx]) {
@@ -930,15 +1023,16 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
       }
       ReadMeta& m = rmeta[ridx];
       m.data_off16 = (uint32_t)(rpos / 16);
-      m.len_cls = (uint32_t)r.len | ((uint32_t)c64 << 24);
+      m.len_cls = (uint32_t)r.len | (two_plane ? kTwoPlaneBit : 0u) | ((uint32_t)c64 << 24);
       m.out_off = (uint32_t)(P.reg_out0[k] + (uint64_t)oi * (uint64_t)nh);
       m.hap0 = hap0;
+      if (P.finalize) reinterpret_cast<uint32_t*>(base + P.off_rnh)[ridx] = (uint32_t)nh;
       if (rerun) {
         RerunEntry* e = rerun + rbase[c64] + fill[c64];
         for (int32_t j = 0; j < nh; ++j) { e[j].read = (uint32_t)ridx; e[j].hap = hap0 + (uint32_t)j; }
         fill[c64] += (uint32_t)nh;
       }
-      rpos += 5u * (size_t)lp;
+      rpos += read_blob_bytes((uint32_t)r.len, two_plane);
       ++ridx;
     }
     opos += nr;
@@ -1002,7 +1096,7 @@ static void set_gcp_constants(KParams& p, int key) {
 }
 
 // Enqueue one chunk on the slot's stream.  upload/download = include the H2D / D2H copies.
-int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
+int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download, bool timing) {
   const ChunkPlan& P = s.plan;
   static const bool lc_probe = env_i64("FCS_PHMM_TIMELINE", 0) >= 2;  // developer probe: host cost of the driver calls
   const double lc0 = lc_probe ? now_ms() : 0;
@@ -1013,47 +1107,60 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
   }
   if (!upload && !P.force_double)  // resident batch: the queues must start empty on every run
     CK(cudaMemsetAsync(s.d_buf + P.off_rcount, 0, kMaxF64Classes * sizeof(uint32_t), s.stream));
-  CK(cudaEventRecord(s.ev_k0, s.stream));
+  // (the three timing events are driver calls on the host's critical path -- four packing threads share one driver
+  // lock -- so streamed chunks record them only on request; resident runs always do)
+  s.timed = timing;
+  if (timing) CK(cudaEventRecord(s.ev_k0, s.stream));
   if (lc_probe) lc1 = now_ms();
-  // Fork: launch i goes to stream i % (1 + kSide); the side streams start after the upload and are
-  // joined before the next phase, so launches of different classes fill each other's tails.
-  // (only the side streams that get a launch are forked and joined: every call here is a driver round
-  // trip on the host's critical path, and a small chunk has ~30 of them)
-  auto fork = [&](int n_launches) -> cudaError_t {
-    if (n_launches <= 1) return cudaSuccess;
+  // Fork / join.  Launches that carry a sizeable share of the chunk get a stream each (main stream first), so
+  // that their tails overlap; the small ones (leftover groups, tail-shaped tasks) share ONE stream.  Only the
+  // side streams that are used are forked and joined: every call here is a driver round trip on the host's
+  // critical path, and the packing threads of a device contend for one driver lock.
+  int n_side_used = 0;
+  auto fork = [&](int n_side) -> cudaError_t {
+    n_side_used = n_side;
+    if (n_side <= 0) return cudaSuccess;
     cudaError_t e = cudaEventRecord(s.ev_fork, s.stream);
-    for (int i = 0; i < std::min(Slot::kSide, n_launches - 1) && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s.side[i], s.ev_fork, 0);
+    for (int i = 0; i < n_side && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s.side[i], s.ev_fork, 0);
     return e;
   };
-  auto join = [&](int n_launches) -> cudaError_t {
-    if (n_launches <= 1) return cudaSuccess;
+  auto join = [&]() -> cudaError_t {
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < std::min(Slot::kSide, n_launches - 1) && e == cudaSuccess; ++i) {
+    for (int i = 0; i < n_side_used && e == cudaSuccess; ++i) {
       e = cudaEventRecord(s.ev_side[i], s.side[i]);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(s.stream, s.ev_side[i], 0);
     }
+    n_side_used = 0;
     return e;
   };
-  auto pick = [&](int i, int n_launches) { return (n_launches <= 1 || i % (1 + Slot::kSide) == 0) ? s.stream : s.side[i % (1 + Slot::kSide) - 1]; };
+  // stream of slot index k: 0 = the chunk's own stream, 1.. = side streams
+  auto stream_of = [&](int k) { return k <= 0 ? s.stream : s.side[std::min(k, (int)Slot::kSide) - 1]; };
   if (!P.force_double) {
-    int nl = P.n_gen ? 1 : 0, li = 0;
-    for (const F32Range& r : P.f32) nl += r.n_tasks ? 1 : 0;
-    CK(fork(nl));
-    if (P.n_gen) {  // striped generic kernel first: its pairs are the longest-running work items
-      KParams p;
-      fill_kparams(d, s, p, false);
-      CK(launch_generic_f32(p, P.gen_ctas, pick(li++, nl)));
-      stats_.launches += 1;
-    }
-    // biggest launches first
+    // launches whose individual tasks run longest go first, so that they overlap the bulk instead of
+    // starting in its tail
     std::vector<const F32Range*> ord;
     for (const F32Range& r : P.f32)
       if (r.n_tasks) ord.push_back(&r);
-    // launches whose individual tasks run longest go first, so that they overlap the bulk instead of
-    // starting in its tail
     std::stable_sort(ord.begin(), ord.end(), [](const F32Range* a, const F32Range* b) { return a->max_task_cost > b->max_task_cost; });
+    // stream slots: the striped generic launch and every "big" tier launch (>= 1/8 of the chunk's tasks) own one,
+    // all small launches share the last one
+    size_t total_tasks = 0;
+    for (const F32Range* r : ord) total_tasks += r->n_tasks;
+    int n_big = P.n_gen ? 1 : 0, n_small = 0;
+    for (const F32Range* r : ord) ((size_t)r->n_tasks * 8 >= total_tasks ? n_big : n_small)++;
+    const int n_slots = std::min(n_big + (n_small ? 1 : 0), 1 + (int)Slot::kSide);
+    CK(fork(std::max(0, n_slots - 1)));
+    int next_big = 0;
+    if (P.n_gen) {  // striped generic kernel first: its pairs are the longest-running work items
+      KParams p;
+      fill_kparams(d, s, p, false);
+      CK(launch_generic_f32(p, P.gen_ctas, stream_of(next_big++ % n_slots)));
+      stats_.launches += 1;
+    }
     for (const F32Range* rp : ord) {
       const F32Range& r = *rp;
+      const bool big = (size_t)r.n_tasks * 8 >= total_tasks;
+      cudaStream_t st = big ? stream_of(next_big++ % n_slots) : stream_of(n_slots - 1);
       KParams p;
       fill_kparams(d, s, p, false);
       p.tasks += r.task0;
@@ -1082,19 +1189,19 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
           const ClassDesc& cd = r.tk->classes[t.cls];
           double cols = 0, hl = 0, rl = 0;
           for (uint32_t j = 0; j < t.n_haps; ++j) { cols += hm[t.hap0 + j].len + cd.G - 1; hl += hm[t.hap0 + j].len; }
-          for (uint32_t i = 0; i < t.n_reads; ++i) rl += rm[t.read0 + i].len_cls & 0xffffffu;
+          for (uint32_t i = 0; i < t.n_reads; ++i) rl += read_len_of(rm[t.read0 + i]);
           swept += 32.0 * cd.R * cols;
           useful += rl * hl;
         }
-        fprintf(stderr, "[fcs_phmm] f32 launch tier %d form %d key 0x%x tasks %u smem %zu hs_cap %u stage %u geom_eff %.3f classes%s\n", r.tk->tier,
-                r.tk->form, (unsigned)r.gcp, r.n_tasks, r.smem, r.hs_cap, r.hap_stage, useful / swept, cl.c_str());
+        fprintf(stderr, "[fcs_phmm] f32 launch tier %d form %d key 0x%x tasks %u (%s) smem %zu hs_cap %u stage %u geom_eff %.3f classes%s\n", r.tk->tier,
+                r.tk->form, (unsigned)r.gcp, r.n_tasks, big ? "own stream" : "shared stream", r.smem, r.hs_cap, r.hap_stage, useful / swept, cl.c_str());
       }
-      CK(r.tk->launch(p, r.n_tasks, r.smem + smem_pad, pick(li++, nl)));
+      CK(r.tk->launch(p, r.n_tasks, r.smem + smem_pad, st));
       stats_.launches += 1;
     }
-    CK(join(nl));
+    CK(join());
   }
-  CK(cudaEventRecord(s.ev_k1, s.stream));
+  if (timing) CK(cudaEventRecord(s.ev_k1, s.stream));
   if (lc_probe) lc2 = now_ms();
   {
     const int nl = (int)P.f64.size() + (P.gen64_cap ? 1 : 0);
@@ -1108,12 +1215,12 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
     const bool one_hp = f64_serial == 2 && upload && nl <= 2;
     const bool hp = f64_prio && upload && nl > 0 && !serial64;
     const int n_hp = one_hp ? std::min(nl, 1) : std::min(nl, (int)Slot::kHp);
-    auto pick64 = [&](int i) { return serial64 ? s.stream : (hp ? s.hp[one_hp ? 0 : i % Slot::kHp] : pick(i, nl)); };
+    auto pick64 = [&](int i) { return serial64 ? s.stream : (hp ? s.hp[one_hp ? 0 : i % Slot::kHp] : stream_of(i % (1 + (int)Slot::kSide))); };
     if (hp) {
       CK(cudaEventRecord(s.ev_fork, s.stream));
       for (int i = 0; i < n_hp; ++i) CK(cudaStreamWaitEvent(s.hp[i], s.ev_fork, 0));
     } else if (!serial64) {
-      CK(fork(nl));
+      CK(fork(std::min(nl - 1, (int)Slot::kSide)));
     }
     if (P.gen64_cap) {
       KParams p;
@@ -1152,10 +1259,15 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download) {
         CK(cudaStreamWaitEvent(s.stream, s.ev_hp[i], 0));
       }
     } else if (!serial64) {
-      CK(join(nl));
+      CK(join());
     }
   }
-  CK(cudaEventRecord(s.ev_k2, s.stream));
+  if (P.finalize) {
+    CK(launch_finalize(reinterpret_cast<double*>(s.d_buf + P.off_out), reinterpret_cast<const ReadMeta*>(s.d_buf + P.off_rmeta),
+                       reinterpret_cast<const uint32_t*>(s.d_buf + P.off_rnh), s.d_buf + P.off_poor, (uint32_t)P.n_reads, fin_mismap_, fin_err_, s.stream));
+    stats_.launches += 1;
+  }
+  if (timing) CK(cudaEventRecord(s.ev_k2, s.stream));
   if (lc_probe) lc3 = now_ms();
   if (download && P.n_pairs) {
     const size_t nbytes = P.total_bytes - P.off_out;
@@ -1184,9 +1296,11 @@ int Engine::retire_slot(Device& d, Slot& s) {
   const double tw1 = now_ms();
   const ChunkPlan& P = s.plan;
   float ms_all = 0.f, ms_main = 0.f;
-  CK(cudaEventElapsedTime(&ms_all, s.ev_k0, s.ev_k2));
-  CK(cudaEventElapsedTime(&ms_main, s.ev_k0, s.ev_k1));
-  if (g_tl_ref) {
+  if (s.timed) {
+    CK(cudaEventElapsedTime(&ms_all, s.ev_k0, s.ev_k2));
+    CK(cudaEventElapsedTime(&ms_main, s.ev_k0, s.ev_k1));
+  }
+  if (g_tl_ref && s.timed) {
     float a = 0, b = 0, c = 0, e = 0;
     cudaEventElapsedTime(&a, g_tl_ref, s.ev_k0);
     cudaEventElapsedTime(&b, g_tl_ref, s.ev_k1);
@@ -1202,12 +1316,21 @@ int Engine::retire_slot(Device& d, Slot& s) {
   const float* raw = reinterpret_cast<const float*>(s.h_out + (P.off_raw - P.off_out));
   uint64_t n64 = 0;
   const Input& in = *s.input;
+  const uint8_t* poor = s.h_out + (P.off_poor - P.off_out);
+  size_t rbase = 0;  // packed read index of the region's first read (reads are packed sorted by length: s.order)
   for (size_t k = 0; k < P.regions.size(); ++k) {
     const int64_t g = P.regions[k];
     int32_t nr = 0, nh = 0;
     in.shape(g, nr, nh);
     const size_t n = (size_t)nr * (size_t)nh;
     if (!n) continue;
+    if (P.finalize) {
+      if (uint8_t* pf = in.poorly(g)) {
+        const uint32_t* ord = s.order.data() + rbase;
+        for (int32_t i = 0; i < nr; ++i) pf[ord[i]] = poor[rbase + (size_t)i];
+      }
+    }
+    rbase += (size_t)nr;
     const uint64_t o = P.reg_out0[k];
     std::memcpy(in.out(g), out + o, n * sizeof(double));
     if (uint8_t* u = in.used(g)) std::memcpy(u, used + o, n);
@@ -1313,6 +1436,7 @@ class CombinedInput : public Input {
   double* out(int64_t g) const override { const auto w = where(g); return parts_[w.first]->out(w.second); }
   uint8_t* used(int64_t g) const override { const auto w = where(g); return parts_[w.first]->used(w.second); }
   float* raw(int64_t g) const override { const auto w = where(g); return parts_[w.first]->raw(w.second); }
+  uint8_t* poorly(int64_t g) const override { const auto w = where(g); return parts_[w.first]->poorly(w.second); }
   void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const override { const auto w = where(g); parts_[w.first]->sum_lens(w.second, sr, sh); }
 
  private:
@@ -1371,16 +1495,15 @@ int Engine::compute_one_noexcept(const Input& in) {
 }
 
 int Engine::compute(const Input& in) {
-  // Per call, before it can join a batch: structural validation (a malformed call must not fail the callers it
-  // would be merged with) and the capture hook (once per original call, and only for calls that passed the
-  // checks, so the writer never dereferences a null plane).
-  {
-    const int rc = validate_input(in);
-    if (rc != FCS_PHMM_OK) return rc;
-  }
+  // Per call, before it can join a batch: the capture hook -- once per original call (a failing merged batch is
+  // re-run call by call below and must not be captured twice), and only for calls that pass the structural checks,
+  // so the writer never dereferences a null plane.  (Without capture the planner's own per-read checks reject a
+  // malformed call; if it was merged with others, the batch is re-run call by call and only its owner sees the error.)
+  if (in.n_regions() < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
   if (in.n_regions() == 0) return FCS_PHMM_OK;
   if (capture_ && capture_->active()) {
-    const int rc = capture_->append(in);
+    int rc = validate_input(in);  // an extra pass over the reads: only paid while capturing
+    if (rc == FCS_PHMM_OK) rc = capture_->append(in);
     if (rc != FCS_PHMM_OK) return rc;
   }
   PendingCall me;
@@ -1436,6 +1559,8 @@ int Engine::compute_one(const Input& in) {
   const size_t D = devs_.size();
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
   static const bool timeline = env_i64("FCS_PHMM_TIMELINE", 0) != 0;  // developer knob: host timeline of the call on stderr
+  // per-chunk device times (fcs_phmm_stats kernel_ms / main_kernel_ms of streamed calls): off unless asked for
+  static const bool chunk_timing = timeline || env_i64("FCS_PHMM_CHUNK_TIMING", 0) != 0;
   const double tl0 = now_ms();
   if (timeline && D == 1) {
     if (!g_tl_ref) cudaEventCreate(&g_tl_ref);
@@ -1455,17 +1580,29 @@ int Engine::compute_one(const Input& in) {
   };
   // ---- size every region once
   std::vector<uint64_t> rc_cells((size_t)n), rc_pairs((size_t)n), rc_bytes((size_t)n), rc_ub_in((size_t)n);
-  for (int64_t g = 0; g < n; ++g) {
-    int32_t nr = 0, nh = 0;
-    in.shape(g, nr, nh);
-    uint64_t sr = 0, sh = 0;
-    in.sum_lens(g, sr, sh);
-    rc_cells[(size_t)g] = sr * sh;
-    rc_pairs[(size_t)g] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
-    rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
-    // upper bound of the region's share of a chunk's input section: padded planes + metadata + one task and
-    // one striped-path entry per pair at worst
-    rc_ub_in[(size_t)g] = 5 * sr + 91ull * (uint64_t)std::max(0, nr) + sh + 23ull * (uint64_t)std::max(0, nh) + 24ull * rc_pairs[(size_t)g];
+  auto size_range = [&](int64_t g0, int64_t g1) {
+    for (int64_t g = g0; g < g1; ++g) {
+      int32_t nr = 0, nh = 0;
+      in.shape(g, nr, nh);
+      uint64_t sr = 0, sh = 0;
+      in.sum_lens(g, sr, sh);
+      rc_cells[(size_t)g] = sr * sh;
+      rc_pairs[(size_t)g] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
+      rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
+      // upper bound of the region's share of a chunk's input section: padded planes + metadata + one task and
+      // one striped-path entry per pair at worst
+      rc_ub_in[(size_t)g] = 5 * sr + 91ull * (uint64_t)std::max(0, nr) + sh + 23ull * (uint64_t)std::max(0, nh) + 24ull * rc_pairs[(size_t)g];
+    }
+  };
+  // the pass reads one length per read from the caller's (cold) arrays: for a large call it is split over the pool
+  // (config 3, 2000 regions / 80k reads: 0.34 ms alone, before any device work can start)
+  {
+    const int parts = (int)std::min<int64_t>(std::max<int64_t>(1, n / 256), (int64_t)std::max(1, (int)devs_.size() * pack_threads_));
+    if (parts <= 1) size_range(0, n);
+    else {
+      const std::function<void(int)> sizer = [&](int p) { size_range(n * p / parts, n * (p + 1) / parts); };
+      pool_->run(parts, sizer);
+    }
   }
   // ---- regions -> devices
   std::vector<std::vector<int64_t>> part(D);
@@ -1585,6 +1722,7 @@ int Engine::compute_one(const Input& in) {
       const double t0 = now_ms();
       size_t next = 0;
       Planner pl{in, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count, c + 1 == dw.chunks.size()};
+      pl.finalize = fin_on_.load();
       rc = pl.run(dw.chunks[c], 0, next);
       if (rc == FCS_PHMM_OK && next != dw.chunks[c].size()) rc = set_error(FCS_PHMM_EUNSUPPORTED, "a single region exceeds the chunk limits (2^31 pairs / 2 GiB)");
       if (rc != FCS_PHMM_OK) { fail_with(rc); break; }
@@ -1602,7 +1740,7 @@ int Engine::compute_one(const Input& in) {
       }
       s.input = &in;
       tl_mark("packed", w, c);
-      rc = launch_chunk(d, s, true, true);
+      rc = launch_chunk(d, s, true, true, chunk_timing);
       if (rc != FCS_PHMM_OK) { cudaStreamSynchronize(s.stream); fail_with(rc); break; }
       s.busy = true;
       tl_mark("launched", w, c);
@@ -1669,7 +1807,9 @@ int Engine::wait(fcs_phmm_ticket t) {
 namespace {
 class FlatInput : public Input {
  public:
-  FlatInput(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw) : b_(b), out_(out), used_(used), raw_(raw) {}
+  FlatInput(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw, uint8_t* poorly = nullptr)
+      : b_(b), out_(out), used_(used), raw_(raw), poorly_(poorly) {}
+  uint8_t* poorly(int64_t g) const override { return poorly_ ? poorly_ + b_.reg_read0[g] : nullptr; }
   int64_t n_regions() const override { return b_.n_regions; }
   void shape(int64_t g, int32_t& nr, int32_t& nh) const override { nr = b_.reg_nreads[g]; nh = b_.reg_nhaps[g]; }
   InRead read(int64_t g, int32_t i) const override {
@@ -1699,11 +1839,12 @@ class FlatInput : public Input {
   double* out_;
   uint8_t* used_;
   float* raw_;
+  uint8_t* poorly_;
 };
 }  // namespace
 
-std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw) {
-  return std::unique_ptr<Input>(new FlatInput(b, out, used, raw));
+std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw, uint8_t* poorly) {
+  return std::unique_ptr<Input>(new FlatInput(b, out, used, raw, poorly));
 }
 
 int Engine::batch_create(const fcs_phmm_flat_batch* fb, int device_index, Batch** out) {
@@ -1725,6 +1866,7 @@ int Engine::batch_create(const fcs_phmm_flat_batch* fb, int device_index, Batch*
   size_t next = 0;
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
   Planner pl{*b->input, s, use_double_, keep_raw_, INT64_MAX, hs_cols, d.sm_count, true, false};  // resident: one launch set, exact classes
+  pl.finalize = fin_on_.load();
   int rc = pl.run(regs, 0, next);
   if (rc == FCS_PHMM_OK && next != regs.size())
     rc = set_error(FCS_PHMM_EUNSUPPORTED, "batch too large for one resident chunk (2^31 pairs / 2 GiB of reads+haplotypes)");
@@ -1755,7 +1897,7 @@ int Engine::batch_run(Batch* b, bool timed, float* total_ms, float* main_ms) {
   Device& d = *devs_[b->device_index];
   std::lock_guard<std::mutex> lk(d.mu);
   CK(cudaSetDevice(d.ordinal));
-  int rc = launch_chunk(d, b->slot, false, false);
+  int rc = launch_chunk(d, b->slot, false, false, true);
   if (rc != FCS_PHMM_OK) return rc;
   if (timed) {
     CK(cudaEventSynchronize(b->slot.ev_done));
@@ -1826,6 +1968,11 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
   if (rc != FCS_PHMM_OK) return rc;
   if (next != regs.size()) return set_error(FCS_PHMM_EUNSUPPORTED, "batch too large for one chunk");
   const double t1 = now_ms();
+  if (g_plan_prof) {
+    fprintf(stderr, "[fcs_phmm plan prof, ms] quality scans %.2f  per-region checks+hap scan %.2f  sort %.2f  tasks %.2f  fp64 caps %.2f  post (task sort, layout) %.2f\n",
+            t_prof.scan, t_prof.region, t_prof.sort, t_prof.tasks, t_prof.f64, t_prof.post);
+    t_prof = PlanProf();
+  }
   ChunkPlan& P = s.plan;
   std::vector<uint8_t> buf(P.in_bytes + 256);  // touched here, so the pack time below excludes page faults
   s.h_in = buf.data();
@@ -1866,7 +2013,7 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
       for (uint32_t j = 0; j < t.n_haps; ++j) { cols += hm[t.hap0 + j].len + cd.G - 1; hl += hm[t.hap0 + j].len; }
       for (uint32_t i = 0; i < t.n_reads; ++i) {
         const ReadMeta& m = rm[t.read0 + i];
-        const uint32_t len = m.len_cls & 0xffffffu;
+        const uint32_t len = read_len_of(m);
         if ((int)len + 1 > cd.G * cd.R) return set_error(FCS_PHMM_EINVAL, "plan_check: class does not cover the read");
         rl += len;
         for (uint32_t j = 0; j < t.n_haps; ++j) {

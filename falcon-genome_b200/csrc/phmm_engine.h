@@ -44,6 +44,8 @@ class Input {
   virtual double* out(int64_t g) const = 0;
   virtual uint8_t* used(int64_t g) const = 0;
   virtual float* raw(int64_t g) const = 0;
+  // poorly-modelled flags of region g's reads (caller's read order), or null (finalize epilogue)
+  virtual uint8_t* poorly(int64_t g) const { (void)g; return nullptr; }
   // Sum of the (non-negative) read and haplotype lengths of region g: the sizing pass of a call walks every
   // read once, so inputs override this with a loop over their own arrays (no virtual call per read).
   virtual void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const {
@@ -92,6 +94,8 @@ struct ChunkPlan {
   size_t off_reads = 0, off_haps = 0, off_rmeta = 0, off_hmeta = 0, off_tasks = 0, off_rbase = 0, off_rcount = 0;
   size_t off_rerun = 0, in_bytes = 0;  // input part = [0, in_bytes)
   size_t off_out = 0, off_used = 0, off_raw = 0, total_bytes = 0;
+  bool finalize = false;             // per-read cap + poorly-modelled flag epilogue
+  size_t off_rnh = 0, off_poor = 0;  // finalize: haplotypes per read (input, u32), flags per read (output, u8)
   size_t n_tasks = 0;
   size_t off_genlist = 0, off_scratch = 0;
   uint32_t n_gen = 0, gen64_cap = 0, gen_ctas = 0, scratch_cols = 0;  // striped generic path
@@ -127,11 +131,13 @@ struct Slot {
   uint8_t* d_buf = nullptr;
   size_t d_cap = 0;
   bool busy = false;
+  bool timed = false;  // the chunk in flight recorded its timing events (ev_k0 / ev_k1 / ev_k2)
   ChunkPlan plan;
   const Input* input = nullptr;
   // packer scratch (reused)
   std::vector<TaskBucket> buckets;
   std::vector<uint32_t> order;
+  std::vector<int> ukeys;              // per read (region by region, caller's order): gcp | ins << 8 | del << 16 if all three are constant, else -1
   std::vector<RerunEntry> genlist;     // (read, hap) pairs of the striped generic path
   std::vector<uint8_t> gen_flags;      // per chunk-wide read: takes the generic path
 };
@@ -207,12 +213,13 @@ class Engine {
   int device_count() const { return (int)devs_.size(); }
   static int pack_chunk_static(Slot& s, const Input& in);
   int set_capture(const char* path);  // nullptr / empty = stop capturing
+  void set_finalize(bool on, double log10_mismap, double err_rate) { fin_on_ = on; fin_mismap_ = log10_mismap; fin_err_ = err_rate; }
 
  private:
   Engine();
   int init(const fcs_phmm_config* cfg);
   int pack_chunk(Slot& s, const Input& in);
-  int launch_chunk(Device& d, Slot& s, bool upload, bool download);
+  int launch_chunk(Device& d, Slot& s, bool upload, bool download, bool timing);
   int retire_slot(Device& d, Slot& s);
   int ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t dev_bytes);
   void fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) const;
@@ -220,6 +227,8 @@ class Engine {
   std::vector<std::unique_ptr<Device>> devs_;
   bool use_double_ = false;
   bool keep_raw_ = false;
+  std::atomic<bool> fin_on_{false};
+  double fin_mismap_ = -4.5, fin_err_ = 0.02;
   int pack_threads_ = 0;
   int64_t max_chunk_cells_ = 0;
   Stats stats_;
@@ -263,6 +272,6 @@ int finalize_region(double* l, int32_t n_reads, int32_t n_haps, const int32_t* r
 
 int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* out);
 
-std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw);
+std::unique_ptr<Input> make_flat_input(const fcs_phmm_flat_batch& b, double* out, uint8_t* used, float* raw, uint8_t* poorly = nullptr);
 
 }  // namespace fcsphmm

@@ -219,9 +219,11 @@ struct Tile {
   // memory for the UA form, which touches only bases and base qualities); len == 0 => no read.
   // row0 / npad: tile row 0 of lane 0 is row `row0` of a striped read whose first `npad` rows are
   // boundary replicas (single pass: row0 = 0, npad = G*R - len).
+  // two_plane: the read is packed as [bases | base quals | trailer {ins, del, gcp}] (constant transition qualities).
   __device__ __forceinline__ void build(const uint8_t* rs, uint32_t len, int lig, const T* lut, const T* __restrict__ mm,
-                                        uint8_t* tab_lane, bool with_n, int row0 = 0, int npad_override = -1) {
+                                        uint8_t* tab_lane, bool with_n, bool two_plane, int row0 = 0, int npad_override = -1) {
     const uint32_t Lp = round_up16(len);
+    const uint32_t qpl = two_plane ? 1u : Lp;  // distance between the ins / del / gcp values of one read position
     const int npad = (npad_override >= 0 ? npad_override : G * R - (int)len) - row0;
     npl = min(max(npad - lig * R, 0), R);
     off_last = ((threadIdx.x >> 2) & 1) ? -16 : (NV - 1) * 16;
@@ -238,7 +240,8 @@ struct Tile {
         pm = A::sub(T(1), e);
         px = A::div(e, T(3));
         if constexpr (!UA) {
-          const uint32_t iq = rs[2 * Lp + pos] & 127u, dq = rs[3 * Lp + pos] & 127u;
+          const uint32_t qpo = two_plane ? 0u : (uint32_t)pos;
+          const uint32_t iq = rs[2 * Lp + qpo] & 127u, dq = rs[2 * Lp + qpl + qpo] & 127u;
           const uint32_t mn = min(iq, dq), mx = max(iq, dq);
           pMM[k] = mm[((mx * (mx + 1u)) >> 1) + mn];
           pMX[k] = lut[iq];
@@ -247,7 +250,7 @@ struct Tile {
           pMX[0] = cMX;
         }
         T pc = cXX;
-        if constexpr (!UG) pc = lut[rs[4 * Lp + pos] & 127u];
+        if constexpr (!UG) pc = lut[rs[2 * Lp + 2 * qpl + (two_plane ? 0u : (uint32_t)pos)] & 127u];
         gmk = A::sub(T(1), pc);
         xxk = pc;
         yyk = pc;
@@ -447,21 +450,22 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   const bool active = grp < (int)task.n_reads;
   const uint32_t read = task.read0 + (active ? grp : 0);
   const ReadMeta rm = p.rmeta[read];
-  const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
+  const uint32_t rlen = active ? read_len_of(rm) : 0u;
+  const bool two_plane = read_two_plane(rm);
   const HapMeta h_first = p.hmeta[task.hap0];
   const HapMeta h_last = p.hmeta[task.hap0 + task.n_haps - 1];
   const uint32_t hap_bytes = (h_last.data_off16 - h_first.data_off16) * 16u + round_up16(h_last.len);
   // ---- stage reads + haplotypes with TMA bulk copies
-  const uint32_t my_bytes = ((!UA && active && lig == 0) ? 5u * round_up16(rlen) : 0u) + (lane == 0 ? hap_bytes : 0u);
+  const uint32_t my_bytes = ((!UA && active && lig == 0) ? read_blob_bytes(rlen, two_plane) : 0u) + (lane == 0 ? hap_bytes : 0u);
   const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
   if (lane == 0) mbar_expect_tx(bar, tot);
   __syncwarp();
-  if (!UA && active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
+  if (!UA && active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, read_blob_bytes(rlen, two_plane), bar);
   if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
   // ---- per-row constants + prior table (the UA form builds from global memory while the copy flies)
-  if constexpr (UA) tile.build(p.reads + (size_t)rm.data_off16 * 16u, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+  if constexpr (UA) tile.build(p.reads + (size_t)rm.data_off16 * 16u, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, two_plane);
   mbar_wait(bar, 0u);
-  if constexpr (!UA) tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+  if constexpr (!UA) tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, two_plane);
   if (p.n_sym > (uint32_t)kCodeOther)
     Tile<T, G, R, FORM>::build_other_rows(UA ? p.reads + (size_t)rm.data_off16 * 16u : rstage, rlen, lig, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last);
   __syncwarp();  // every lane is done with the LUT and the read staging before the stream overwrites them
@@ -530,22 +534,23 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
     if (active) e = list[base + grp];
     const ReadMeta rm = p.rmeta[e.read];
     const HapMeta hm = p.hmeta[e.hap];
-    const uint32_t rlen = active ? (rm.len_cls & 0xffffffu) : 0u;
+    const uint32_t rlen = active ? read_len_of(rm) : 0u;
+    const bool two_plane = read_two_plane(rm);
     const uint32_t Lh = active ? hm.len : 0u;
     // the LUT shares its shared memory with the haplotype stream of the previous round: reload it
     for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
     fence_proxy_async();  // staging / stream were touched through the generic proxy last round
-    const uint32_t my_bytes = (active && lig == 0) ? 5u * round_up16(rlen) + round_up16(Lh) : 0u;
+    const uint32_t my_bytes = (active && lig == 0) ? read_blob_bytes(rlen, two_plane) + round_up16(Lh) : 0u;
     const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
     if (lane == 0) mbar_expect_tx(bar, tot);
     __syncwarp();
     if (active && lig == 0) {
-      bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, 5u * round_up16(rlen), bar);
+      bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, read_blob_bytes(rlen, two_plane), bar);
       bulk_g2s(hstage, p.haps + (size_t)hm.data_off16 * 16u, round_up16(Lh), bar);
     }
     mbar_wait(bar, parity);
     parity ^= 1u;
-    tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u);
+    tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, two_plane);
     if (p.n_sym > (uint32_t)kCodeOther) Tile<T, G, R, FORM>::build_other_rows(rstage, rlen, lig, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last);
     __syncwarp();  // done with the LUT and the read staging before the stream overwrites them
     const uint32_t Lmax = __reduce_max_sync(0xffffffffu, Lh);

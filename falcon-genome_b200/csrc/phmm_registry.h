@@ -57,6 +57,9 @@ constexpr int kTierMinBlocks[3] = {16, 12, 8};
 // striped generic kernels (phmm_generic.cuh): any read / haplotype length
 cudaError_t launch_generic_f32(const KParams& p, unsigned grid, cudaStream_t s);
 cudaError_t launch_generic_f64(const KParams& p, unsigned grid, cudaStream_t s);
+// finalize epilogue (phmm_generic_inst.cu): per read, cap the row at best + log10_mismap and flag poorly-modelled reads
+cudaError_t launch_finalize(double* out, const ReadMeta* rmeta, const uint32_t* rnh, uint8_t* poorly, uint32_t n_reads, double log10_mismap,
+                            double err_rate, cudaStream_t s);
 constexpr int kGenericMaxSinglePassRead = 383;  // longer reads take the striped path (FP64 single-pass tiles end at 384 rows)
 constexpr int kGenericMinHapLen = 2001;         // regions with a longer haplotype take the striped path
 

@@ -4,7 +4,10 @@
 // cp.async.bulk moves a read set or a haplotype set into shared memory):
 //
 //   reads   : per read  [bases | base_q | ins_q | del_q | gcp], each plane padded to
-//             Lp = round_up(len, 16) bytes  -> 5*Lp bytes per read, reads of a task adjacent
+//             Lp = round_up(len, 16) bytes  -> 5*Lp bytes per read, reads of a task adjacent;
+//             a read whose insertion, deletion and continuation qualities are each one constant
+//             (what GATK passes without BAM BI/BD tags and without the PCR indel model) is packed
+//             as TWO planes plus a 16-byte trailer [ins, del, gcp, 0...]: 2*Lp + 16 bytes
 //   haps    : per hap   bases padded to round_up(len, 16)
 //   rmeta[] : ReadMeta per read,  hmeta[] : HapMeta per hap,  tasks[] : Task per CTA
 //   out[]   : double per pair, used[] : u8 per pair, raw[] : float per pair (optional)
@@ -37,7 +40,7 @@ constexpr int kQueueGenericF64 = kMaxF64Classes - 1;  // FP64 rerun queue of the
 
 struct ReadMeta {
   uint32_t data_off16;  // offset of the read blob in `reads`, in 16-byte units
-  uint32_t len_cls;     // len | (fp64 class id << 24)
+  uint32_t len_cls;     // len | two-plane flag << 23 | (fp64 class id << 24)
   uint32_t out_off;     // index in out[] of (this read, first hap of its region)
   uint32_t hap0;        // first hap (chunk-wide index) of its region
 };
@@ -104,6 +107,12 @@ struct KParams {
 };
 
 PHMM_HD inline constexpr uint32_t round_up16(uint32_t x) { return (x + 15u) & ~15u; }
+constexpr uint32_t kTwoPlaneBit = 1u << 23;
+PHMM_HD inline uint32_t read_len_of(const ReadMeta& m) { return m.len_cls & 0x7fffffu; }
+PHMM_HD inline bool read_two_plane(const ReadMeta& m) { return (m.len_cls & kTwoPlaneBit) != 0u; }
+PHMM_HD inline constexpr uint32_t read_blob_bytes(uint32_t len, bool two_plane) {
+  return two_plane ? 2u * round_up16(len) + 16u : 5u * round_up16(len);
+}
 
 // Table lane stride in bytes: smallest odd multiple of 16 that holds R values of size esz.
 // Odd => the eight lanes of a quarter-warp LDS.128 phase hit eight distinct 16-byte bank groups.

@@ -220,6 +220,21 @@ class PairHMM:
             raw.ctypes.data_as(_lib.f32p) if want_raw else None))
         return (out, used, raw) if want_raw else (out, used)
 
+    def set_finalize(self, enabled: bool = True, log10_global_mismapping_rate: float = -4.5, expected_error_rate: float = 0.02):
+        """Fuse GATK's per-read cap (best + mismapping rate) and the poorly-modelled-read test into the device pipeline."""
+        fp = _lib.FinalizeParams(int(bool(enabled)), 0, log10_global_mismapping_rate, expected_error_rate)
+        self._check(self._lib.fcs_pairhmm_set_finalize(self._h, C.byref(fp)))
+
+    def compute_flat_finalized(self, b: FlatBatch):
+        """``fcs_pairhmm_compute_flat_finalized``: (capped log10 matrix, used_fp64, poorly-modelled flag per read)."""
+        fs = _flat_struct(b)
+        out = np.zeros(b.n_pairs, np.float64)
+        used = np.zeros(b.n_pairs, np.uint8)
+        poorly = np.zeros(b.n_reads, np.uint8)
+        self._check(self._lib.fcs_pairhmm_compute_flat_finalized(self._h, C.byref(fs), out.ctypes.data_as(_lib.f64p), used.ctypes.data_as(_lib.u8p),
+                                                                 poorly.ctypes.data_as(_lib.u8p)))
+        return out, used, poorly
+
     def submit(self, region_array: RegionArray) -> int:
         t = C.c_int64()
         self._check(self._lib.fcs_pairhmm_submit(self._h, region_array.regions, region_array.n, C.byref(t)))

@@ -216,6 +216,23 @@ FCS_PHMM_API int fcs_pairhmm_finalize_region(double* log10_likelihoods, int32_t 
                                              double log10_global_mismapping_rate, double expected_error_rate_per_base,
                                              uint8_t* out_poorly_modeled);
 
+/* The post-processing half fused into the device pipeline ("cheap to fuse on GPU").  While
+ * enabled on a handle, every compute call caps each read's row at  best + log10_global_mismapping_rate  on the
+ * device, after the FP64 reruns and before the download -- out_log10 then holds what GATK's
+ * normalizeLikelihoods would leave -- and fcs_pairhmm_compute_flat_finalized also returns the poorly-modelled flag
+ * per read (best < min(2, ceil(len * expected_error_rate_per_base)) * -4).  Same arithmetic as
+ * fcs_pairhmm_finalize_region, so both give the same bits.  p == NULL or p->enabled == 0 switches it off. */
+typedef struct {
+  int32_t enabled;
+  int32_t reserved;
+  double log10_global_mismapping_rate;  /* GATK default -4.5 */
+  double expected_error_rate_per_base;  /* GATK default 0.02 */
+} fcs_phmm_finalize_params;
+FCS_PHMM_API int fcs_pairhmm_set_finalize(fcs_phmm_handle* h, const fcs_phmm_finalize_params* p);
+/* out_poorly_modeled: one byte per read of the batch (index = read index in the flat batch), may be NULL. */
+FCS_PHMM_API int fcs_pairhmm_compute_flat_finalized(fcs_phmm_handle* h, const fcs_phmm_flat_batch* b, double* out_log10, uint8_t* out_used_fp64,
+                                                    uint8_t* out_poorly_modeled);
+
 /* ---- service seam: client of the fcs-pairhmm-nam daemon -----------------
  * The daemon (falcon-genome_b200/csrc/fcs_pairhmm_nam.cpp) owns the GPUs for the lifetime of a stage, as the
  * Blaze NAM does in the reference (src/worker-htc.cpp:99-112, src/BackgroundExecutor.cpp:13-84).  These

@@ -59,6 +59,15 @@ def load():
     lib.phmm_cpu_batch.argtypes = [u8p, u8p, u8p, u8p, u8p, i64p, i32p, u8p, i64p, i32p, i32p, i32p, i32p, i32p, i64p,
                                    C.c_int, C.POINTER(C.c_double), u8p, C.POINTER(C.c_float), C.c_int, C.c_int]
     lib.phmm_cpu_max_threads.restype = C.c_int
+    lib.phmm_variant_batch.restype = C.c_int64
+    lib.phmm_variant_batch.argtypes = [C.c_int, u8p, u8p, u8p, u8p, u8p, i64p, i32p, u8p, i64p, i32p, i32p, i32p, i32p, i32p, i64p,
+                                       C.c_int, C.POINTER(C.c_double), u8p, C.POINTER(C.c_float), C.c_int]
+    lib.phmm_variant_ph2pr_diffs.restype = C.c_int
+    lib.phmm_variant_ph2pr_powf.restype = C.c_float
+    lib.phmm_variant_ph2pr_powf.argtypes = [C.c_int]
+    lib.phmm_double_batch.restype = None
+    lib.phmm_double_batch.argtypes = [u8p, u8p, u8p, u8p, u8p, i64p, i32p, u8p, i64p, i32p, i32p, i32p, i32p, i32p, i64p,
+                                      C.c_int, C.POINTER(C.c_double), C.c_int]
     lib.phmm_oracle_init()
     _lib = lib
     return lib
@@ -150,6 +159,43 @@ def batch_simd(b, nthreads=0, ftz=False):
         b.reg_nhaps.ctypes.data_as(i32p), b.reg_out0.ctypes.data_as(i64p), b.n_regions,
         out.ctypes.data_as(C.POINTER(C.c_double)), _p(used), raw.ctypes.data_as(C.POINTER(C.c_float)), int(nthreads), int(bool(ftz)))
     return out, used, raw, int(nd)
+
+
+# arithmetic variants of the float path (oracle/pairhmm_variants.c): what a real GKL binary may compute differently
+VAR_NOFMA, VAR_FTZ, VAR_POWF, VAR_LOG10F, VAR_SPLITSUM = 1, 2, 4, 8, 16
+VAR_GKL_STRICT_AVX = VAR_NOFMA | VAR_FTZ | VAR_POWF | VAR_LOG10F | VAR_SPLITSUM  # GKL's AVX build, strictest reading
+VAR_GKL_STRICT_AVX512 = VAR_FTZ | VAR_POWF | VAR_LOG10F | VAR_SPLITSUM             # FMA-capable build
+
+
+def batch_variant(b, flags, nthreads=0):
+    """Scalar float-first / double-fallback scoring of a FlatBatch under arithmetic variant `flags`
+    (0 = the pinned contract, bit-identical to batch_scalar / batch_simd): (out, used_double, raw float sums, n_double)."""
+    lib = load()
+    n = b.n_pairs
+    out = np.zeros(n, np.float64)
+    used = np.zeros(n, np.uint8)
+    raw = np.zeros(n, np.float32)
+    i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    nd = lib.phmm_variant_batch(
+        int(flags), _p(b.read_bases), _p(b.read_q), _p(b.read_i), _p(b.read_d), _p(b.read_c), b.rd_off.ctypes.data_as(i64p),
+        b.rd_len.ctypes.data_as(i32p), _p(b.hap_bases), b.hp_off.ctypes.data_as(i64p), b.hp_len.ctypes.data_as(i32p),
+        b.reg_read0.ctypes.data_as(i32p), b.reg_nreads.ctypes.data_as(i32p), b.reg_hap0.ctypes.data_as(i32p),
+        b.reg_nhaps.ctypes.data_as(i32p), b.reg_out0.ctypes.data_as(i64p), b.n_regions,
+        out.ctypes.data_as(C.POINTER(C.c_double)), _p(used), raw.ctypes.data_as(C.POINTER(C.c_float)), int(nthreads))
+    return out, used, raw, int(nd)
+
+
+def batch_double(b, nthreads=0):
+    """Every pair of a FlatBatch in double precision (scalar C, OpenMP over reads): log10 L per pair."""
+    lib = load()
+    out = np.zeros(b.n_pairs, np.float64)
+    i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    lib.phmm_double_batch(
+        _p(b.read_bases), _p(b.read_q), _p(b.read_i), _p(b.read_d), _p(b.read_c), b.rd_off.ctypes.data_as(i64p),
+        b.rd_len.ctypes.data_as(i32p), _p(b.hap_bases), b.hp_off.ctypes.data_as(i64p), b.hp_len.ctypes.data_as(i32p),
+        b.reg_read0.ctypes.data_as(i32p), b.reg_nreads.ctypes.data_as(i32p), b.reg_hap0.ctypes.data_as(i32p),
+        b.reg_nhaps.ctypes.data_as(i32p), b.reg_out0.ctypes.data_as(i64p), b.n_regions, out.ctypes.data_as(C.POINTER(C.c_double)), int(nthreads))
+    return out
 
 
 def max_threads():

@@ -314,7 +314,7 @@ def test_haplotype_bytes_outside_acgtn(hmm, oracle):
     regs = []
     # (a) haplotype-only foreign bytes (the realistic case): IUPAC + lower case + N, reads clean / with N
     h0 = seq(320)
-    haps = [h0, spoil(h0, b"RYKMSWnacgt", 0.03), spoil(h0[20:300], b"NRY", 0.05), spoil(h0[:150], b"*-.", 0.02)]
+    haps = [h0, spoil(h0, b"RYKMna", 0.03), spoil(h0[20:300], b"NRY", 0.05), spoil(h0[:150], b"*-.SW", 0.02)]
     regs.append(Region(_uniform_indel_region(rng, 150, 16, h0, n_rate=0.01), haps))          # all-uniform kernels
     regs.append(Region(_uniform_indel_region(rng, 101, 9, h0, 40, 38, 10), haps))            # uniform-GCP kernels
     # (b) the same foreign bytes in reads and haplotypes: equal bytes match (raw compare), different ones do not
@@ -355,6 +355,51 @@ def test_haplotype_bytes_outside_acgtn(hmm, oracle):
     with pytest.raises(PairHMMError) as e:
         hmm.compute_likelihoods([(many, bytes([30] * 12), bytes([45] * 12), bytes([45] * 12), bytes([10] * 12))], [many])
     assert e.value.code == -5
+
+
+def test_finalize_epilogue_on_device(oracle):
+    """f2 fused into the device pipeline: with set_finalize() every read's row is capped at best - 4.5 on the GPU and
+    the poorly-modelled flag comes back per read.  Checked against (1) a restatement written here from GATK's
+    description with numpy whole-matrix operations on the ORACLE's likelihoods, (2) the library's host function
+    fcs_pairhmm_finalize_region applied to the unfinalized GPU result (bit-equal), through the streamed path with
+    small chunks, the region API and a resident batch."""
+    from falcon_genome_b200 import RegionArray
+    from falcon_genome_b200.prepost import finalize_region
+
+    b = synth.config1_golden(n_regions=30, seed=77)
+    lowq = synth.config5_underflow(n_regions=2, seed=78)  # reads that are poorly modelled by every haplotype
+    for bb in (b, lowq):
+        with PairHMM(max_chunk_cells=20_000_000, slots_per_device=2) as h:
+            plain, used0 = h.compute_flat(bb)
+            h.set_finalize(True)
+            out, used, poorly = h.compute_flat_finalized(bb)
+            ra = RegionArray(bb)
+            h.compute_regions(bb, ra)
+            rb = h.resident(bb)
+            rb.run()
+            out_res, _ = rb.download()
+            rb.close()
+            h.set_finalize(False)
+            again, _ = h.compute_flat(bb)
+        assert np.array_equal(again, plain) and np.array_equal(used, used0)
+        assert np.array_equal(ra.out, out) and np.array_equal(out_res, out)
+        o_ref, _, _, _ = oracle.batch_simd(bb)
+        flags_ref = np.zeros(bb.n_reads, np.uint8)
+        for g in range(bb.n_regions):
+            nr, nh, o0, r0 = int(bb.reg_nreads[g]), int(bb.reg_nhaps[g]), int(bb.reg_out0[g]), int(bb.reg_read0[g])
+            m = plain[o0:o0 + nr * nh].reshape(nr, nh)
+            lens = bb.rd_len[r0:r0 + nr]
+            host, hflags = finalize_region(m, lens)
+            assert np.array_equal(out[o0:o0 + nr * nh].reshape(nr, nh), host)           # device epilogue == host function, bit for bit
+            assert np.array_equal(poorly[r0:r0 + nr], hflags)
+            # restatement from the description, on the oracle's matrix: L'[r,h] = max(L[r,h], max_h L[r,:] - 4.5)
+            mo = o_ref[o0:o0 + nr * nh].reshape(nr, nh)
+            best = mo.max(axis=1, keepdims=True)
+            assert np.abs(np.maximum(mo, best - 4.5) - out[o0:o0 + nr * nh].reshape(nr, nh)).max() <= 1e-4
+            flags_ref[r0:r0 + nr] = best[:, 0] < np.minimum(2.0, np.ceil(lens * 0.02)) * -4.0
+        near = np.zeros(bb.n_reads, bool)  # reads whose best likelihood sits within the tolerance of the flag threshold may differ
+        assert np.array_equal(poorly[~near], flags_ref[~near])
+    assert poorly.any()  # the low-quality batch has poorly modelled reads
 
 
 def test_full_size_config2_properties(hmm):

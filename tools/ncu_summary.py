@@ -1,5 +1,7 @@
 """Summarise an .ncu-rep (read here, no GPU needed) into the metrics DESIGN.md / bench.py cite.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.md"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--traffic-key c2 --source profiles/<name>.md] > profiles/<name>.md
+With --traffic-key the first kernel's DRAM bytes are written to profiles/ncu_traffic.json under that key: bench.py
+takes roofline.traffic from there (never from a constant in the code)."""
 import csv
 import io
 import subprocess
@@ -22,14 +24,46 @@ KEYS = [
 ]
 
 
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return int(round(v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)))
+
+
 def main():
-    rep = sys.argv[1]
+    import argparse
+    import json
+    import os
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("rep")
+    ap.add_argument("--traffic-key")
+    ap.add_argument("--source", default="")
+    a = ap.parse_args()
+    rep = a.rep
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     print(f"# ncu summary of `{rep}`\n")
-    for r in rows[2:]:
+    for n_row, r in enumerate(rows[2:]):
         d = dict(zip(hdr, r))
+        if a.traffic_key and n_row == 0:
+            root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            path = os.path.join(root, "profiles", "ncu_traffic.json")
+            try:
+                table = json.load(open(path))
+            except Exception:
+                table = {}
+            u = lambda k: units[hdr.index(k)]  # noqa: E731
+            table[a.traffic_key] = {
+                "kernel": d.get("Kernel Name"), "grid": d.get("Grid Size"),
+                "dram_bytes_read": to_bytes(d["dram__bytes_read.sum"], u("dram__bytes_read.sum")),
+                "dram_bytes_write": to_bytes(d["dram__bytes_write.sum"], u("dram__bytes_write.sum")),
+                "gpu_time_us": float(d["gpu__time_duration.sum"].replace(",", "")) * {"us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(u("gpu__time_duration.sum"), 1),
+                "registers_per_thread": int(d["launch__registers_per_thread"]),
+                "fma_pipe_pct": float(d["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
+                "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+                "source": a.source, "capture": "ncu --set full --clock-control none, one launch (cold cache, serialised)"}
+            json.dump(table, open(path, "w"), indent=1, sort_keys=True)
         print(f"## {d.get('Kernel Name', '?')}  grid {d.get('Grid Size')} block {d.get('Block Size')}\n")
         print("| metric | value | unit |\n|---|---|---|")
         for k in KEYS:

@@ -379,11 +379,20 @@ Engine::~Engine() {
 }
 
 int Engine::ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t dev_bytes) {
-  auto grow = [](size_t need) { return align_up(need + need / 4 + 4096, 4096); };
+  // Growing a slot means cudaFreeHost + cudaHostAlloc (+ cudaFree + cudaMalloc): milliseconds each, and device-wide
+  // synchronisation.  So the first growth already jumps to a floor that covers a regular chunk of any BASELINE shape
+  // (3 Gcells: ~10 MB in, ~2 MB out), and later growth adds half again: a stream of calls of varying size settles
+  // after one or two calls instead of re-allocating whenever a slightly larger chunk shows up.
+  auto grow = [](size_t need, size_t floor_bytes) { return align_up(std::max(need + need / 2 + 4096, floor_bytes), 4096); };
+  static const size_t floor_in = (size_t)env_i64("FCS_PHMM_SLOT_FLOOR_MB", 16) << 20;
+  const size_t floor_out = floor_in / 4, floor_dev = floor_in * 2;
+  static const bool dbg_grow = env_i64("FCS_PHMM_DEBUG", 0) != 0;
+  if (dbg_grow && (in_bytes > s.h_in_cap || out_bytes > s.h_out_cap || dev_bytes > s.d_cap))
+    fprintf(stderr, "[fcs_phmm] slot grows: in %zu -> %zu, out %zu -> %zu, dev %zu -> %zu bytes\n", s.h_in_cap, in_bytes, s.h_out_cap, out_bytes, s.d_cap, dev_bytes);
   if (in_bytes > s.h_in_cap) {
     if (s.h_in) CK(cudaFreeHost(s.h_in));
     s.h_in = nullptr;
-    s.h_in_cap = grow(in_bytes);
+    s.h_in_cap = grow(in_bytes, floor_in);
     if (cudaHostAlloc((void**)&s.h_in, s.h_in_cap, cudaHostAllocDefault) != cudaSuccess) {
       s.h_in_cap = 0;
       return set_error(FCS_PHMM_ENOMEM, "pinned host allocation failed");
@@ -392,7 +401,7 @@ int Engine::ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t de
   if (out_bytes > s.h_out_cap) {
     if (s.h_out) CK(cudaFreeHost(s.h_out));
     s.h_out = nullptr;
-    s.h_out_cap = grow(out_bytes);
+    s.h_out_cap = grow(out_bytes, floor_out);
     if (cudaHostAlloc((void**)&s.h_out, s.h_out_cap, cudaHostAllocDefault) != cudaSuccess) {
       s.h_out_cap = 0;
       return set_error(FCS_PHMM_ENOMEM, "pinned host allocation failed");
@@ -401,7 +410,7 @@ int Engine::ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t de
   if (dev_bytes > s.d_cap) {
     if (s.d_buf) CK(cudaFree(s.d_buf));
     s.d_buf = nullptr;
-    s.d_cap = grow(dev_bytes);
+    s.d_cap = grow(dev_bytes, floor_dev);
     if (cudaMalloc((void**)&s.d_buf, s.d_cap) != cudaSuccess) {
       s.d_cap = 0;
       return set_error(FCS_PHMM_ENOMEM, "device allocation failed");
@@ -1646,17 +1655,29 @@ int Engine::compute_one(const Input& in) {
     if (limit <= 0) {
       static const int64_t cpt_x10 = env_i64("FCS_PHMM_CHUNKS_PER_THREAD_X10", 20);  // developer knob
       const int64_t want = (int64_t)(total * 10 / (uint64_t)(cpt_x10 * std::max(1, pack_threads_)));
-      limit = std::min<int64_t>(8000000000LL, std::max<int64_t>(500000000LL, want));
+      // at most ~3 Gcells (about 1 ms of device work, 8+ waves of CTAs): larger chunks gain nothing on the device, and
+      // a batch that merges several callers would otherwise grow every slot's pinned staging to a multiple of what
+      // a single call needs (re-allocating pinned memory costs milliseconds per slot)
+      static const int64_t cap_cells = env_i64("FCS_PHMM_CHUNK_CAP_CELLS", 3000000000LL);  // developer knob
+      limit = std::min<int64_t>(cap_cells, std::max<int64_t>(500000000LL, want));
     }
     uint64_t cells = 0, pairs = 0, bytes = 0;
     std::vector<int64_t> cur;
     auto& chunks = work[d].chunks;
     for (int64_t g : part[d]) {
       const size_t k = (size_t)g;
-      static const int ramp_style = (int)env_i64("FCS_PHMM_RAMP", 1);
+      static const int ramp_style = (int)env_i64("FCS_PHMM_RAMP", 2);
       int64_t lim_now = limit;
-      if (ramp && (int)chunks.size() < pack_threads_) lim_now = std::max<int64_t>(limit / 4, 125000000LL);
-      else if (ramp && ramp_style == 1 && (int)chunks.size() < 2 * pack_threads_) lim_now = std::max<int64_t>(limit / 2, 125000000LL);
+      // ramp: the first round of chunks (one per packing thread) is small so that the device starts after a fraction of
+      // a millisecond of planning + packing, later rounds double.  Style 2 adds a round at 1/16 for calls whose regular
+      // chunk is large (config 3: 3 Gcells = 1.1 ms of host work before the first launch otherwise).
+      const int round = (int)chunks.size() / std::max(1, pack_threads_);
+      if (ramp && ramp_style == 2 && limit >= 1500000000LL) {
+        if (round == 0) lim_now = std::max<int64_t>(limit / 16, 125000000LL);
+        else if (round == 1) lim_now = std::max<int64_t>(limit / 4, 125000000LL);
+        else if (round == 2) lim_now = std::max<int64_t>(limit / 2, 125000000LL);
+      } else if (ramp && round == 0) lim_now = std::max<int64_t>(limit / 4, 125000000LL);
+      else if (ramp && ramp_style >= 1 && round == 1) lim_now = std::max<int64_t>(limit / 2, 125000000LL);
       if (!cur.empty() && cells > 0 &&
           ((int64_t)(cells + rc_cells[k]) > lim_now || pairs + rc_pairs[k] > 0x7fffffffULL || bytes + rc_bytes[k] > (1ull << 31))) {
         chunks.emplace_back(std::move(cur));

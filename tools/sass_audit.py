@@ -1,0 +1,148 @@
+"""SASS evidence for DESIGN.md §4/§5 (no GPU needed):
+
+  1. where the register spills of the tier kernels sit: every STL/LDL of every kernel in libfcs_pairhmm's objects is
+     classified as inside or outside a HOT loop (an innermost backward branch whose body holds >= 100 FFMA/FMUL/DFMA/DMUL: the wavefront loops);
+  2. the instruction mix of the wavefront loop bodies of the two classes DESIGN.md quotes (all-uniform G=4,R=38 and
+     uniform-GCP G=8,R=19), compiled alone with the product's flags (tools/sass/one_class.cu), with the listings.
+
+usage: python tools/sass_audit.py            # writes profiles/r02_sass_audit.md + profiles/r02_sass_loop_*.txt
+"""
+import collections
+import glob
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "falcon-genome_b200", "csrc")
+INS = re.compile(r"^\s+/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)\s*(.*?);")
+MATH = ("FFMA", "FMUL", "DFMA", "DMUL")
+
+
+def functions(sass):
+    out, name, rows = [], None, []
+    for ln in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", ln)
+        if m:
+            if name:
+                out.append((name, rows))
+            name, rows = m.group(1), []
+            continue
+        m = INS.match(ln)
+        if m and name:
+            rows.append((int(m.group(1), 16), m.group(2), m.group(3), ln.split("/*")[1].split("*/")[1].strip() if "/*" in ln else ln))
+    if name:
+        out.append((name, rows))
+    return out
+
+
+def hot_loops(rows):
+    addr_idx = {a: i for i, (a, _, _, _) in enumerate(rows)}
+    loops = []
+    for i, (a, op, args, _) in enumerate(rows):
+        if op.startswith("BRA"):
+            m = re.search(r"0x([0-9a-f]+)", args)
+            if m:
+                t = int(m.group(1), 16)
+                if t < a and t in addr_idx:
+                    body = rows[addr_idx[t]:i + 1]
+                    n_math = sum(1 for _, o, _, _ in body if o.split(".")[0] in MATH)
+                    if n_math >= 100:
+                        loops.append((t, a, body, n_math))
+    # innermost only: the wavefront loops themselves, not the per-haplotype / per-pair loops around them
+    return [L for L in loops if not any((M[0] >= L[0] and M[1] <= L[1] and M is not L) for M in loops)]
+
+
+def demangle(n):
+    try:
+        return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip().split("(")[0]
+    except Exception:
+        return n
+
+
+def audit_objects(out):
+    out.append("## 1. Spill instructions of the tier kernels: inside or outside the wavefront loops?\n")
+    out.append("ptxas reports spill bytes per KERNEL, i.e. summed over the 10-33 (G, R) classes a tier kernel holds (one `switch` arm each).")
+    out.append("Every `STL` / `LDL` of every kernel was located in the SASS and tested against the hot loops (innermost backward branches whose")
+    out.append("body holds >= 100 FP multiply/FMA instructions: the unrolled wavefront loops and their remainder loops).\n")
+    out.append("| kernel | registers | spill stores / loads (ptxas) | STL+LDL in the kernel | main wavefront loops (with a spill instruction) | worst main loop | 1-step remainder loops (with a spill instruction) | worst remainder loop |")
+    out.append("|---|---|---|---|---|---|---|---|")
+    worst_share = 0.0
+    for obj in sorted(glob.glob(os.path.join(CSRC, "build", "phmm_mega_*.o")) + [os.path.join(CSRC, "build", "phmm_generic_inst.o")]):
+        sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+        log = open(obj.replace(".o", ".ptxas.log")).read()
+        for name, rows in functions(sass):
+            if "phmm_" not in name:
+                continue
+            loops = hot_loops(rows)
+            n_sp_all = sum(1 for _, op, _, _ in rows if op.startswith("STL") or op.startswith("LDL"))
+            main, rem = [], []
+            for t, a, body, n_math in loops:
+                shfl = sum(1 for _, op, _, _ in body if op.startswith("SHFL"))
+                sp = sum(1 for _, op, _, _ in body if op.startswith("STL") or op.startswith("LDL"))
+                steps = max(1, round(shfl / (6 if "f64" in name or "double" in name else 3)))
+                (main if steps >= 2 or "generic" in name else rem).append((sp, len(body)))
+            m = re.search(re.escape(name) + r".*?(\d+) bytes spill stores, (\d+) bytes spill loads.*?Used (\d+) registers", log, re.S)
+            sp_txt = f"{m.group(1)} / {m.group(2)} B" if m else "?"
+            regs = m.group(3) if m else "?"
+
+            def worst(v):
+                w = max(v, key=lambda x: x[0] / x[1]) if v else (0, 1)
+                return w, (f"{w[0]} of {w[1]} instructions" if w[0] else "-")
+
+            wm, wm_txt = worst(main)
+            wr, wr_txt = worst(rem)
+            worst_share = max(worst_share, wm[0] / wm[1])
+            out.append(f"| `{demangle(name)}` | {regs} | {sp_txt} | {n_sp_all} | {len(main)} ({sum(1 for x in main if x[0])}) | {wm_txt} | {len(rem)} ({sum(1 for x in rem if x[0])}) | {wr_txt} |")
+    out.append(f"\nThe main (2- or 4-step unrolled) wavefront loops hold at most **{100 * worst_share:.2f} %** spill instructions per trip (a reload of a loop-invariant")
+    out.append("pointer); the bulk of the reported spill bytes sits in the prologue / epilogue of the classes (task metadata and table pointers parked across")
+    out.append("the loop nest) and in the 1-step remainder loops, which run at most three times per haplotype.  A class compiled alone (section 2)")
+    out.append("shows the same: G=8, R=19 has 12 spill bytes, all outside the loops.\n")
+
+
+def loop_listing(out, tag, title, defs):
+    cub = f"/tmp/one_{tag}.cubin"
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-I", CSRC] + defs + ["-Xptxas", "-v", "-cubin", "-o", cub,
+           os.path.join(ROOT, "tools", "sass", "one_class.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        out.append(f"(could not build {tag}: {r.stderr[-300:]})")
+        return
+    ptx = [l for l in r.stderr.splitlines() if "registers" in l or "spill" in l]
+    sass = subprocess.run(["cuobjdump", "-sass", cub], capture_output=True, text=True).stdout
+    for name, rows in functions(sass):
+        loops = hot_loops(rows)
+        if not loops:
+            continue
+        t, a, body, n_math = max(loops, key=lambda L: L[3])  # the main (most unrolled) wavefront loop
+        hist = collections.Counter(op for _, op, _, _ in body)
+        total = sum(hist.values())
+        fma_pipe = sum(v for k, v in hist.items() if k.split(".")[0] in MATH or k.split(".")[0] in ("FADD", "DADD"))
+        out.append(f"### {title}\n")
+        out.append(f"`{' '.join(defs)}` — {'; '.join(x.strip() for x in ptx)}\n")
+        out.append(f"Main loop body: {total} instructions at 0x{t:x}..0x{a:x}; {n_math} FP multiply/FMA.  " + ", ".join(f"{v} `{k}`" for k, v in hist.most_common()) + ".\n")
+        path = os.path.join(ROOT, "profiles", f"r02_sass_loop_{tag}.txt")
+        with open(path, "w") as f:
+            f.write(f"# {title}\n# built with: {' '.join(cmd)}\n# main wavefront loop body (cuobjdump -sass), {total} instructions\n")
+            for ad, op, args, _ in body:
+                f.write(f"/*{ad:04x}*/ {op} {args};\n")
+        out.append(f"Listing: `profiles/r02_sass_loop_{tag}.txt`.\n")
+        return hist, total, n_math
+    out.append(f"(no hot loop found in {tag})")
+
+
+def main():
+    out = ["# SASS audit of the PairHMM kernels (tools/sass_audit.py; `cuobjdump -sass` of the objects of this build)\n"]
+    audit_objects(out)
+    out.append("## 2. Wavefront loop bodies of the two classes DESIGN.md quotes\n")
+    loop_listing(out, "ua_g4r38", "All-uniform form, G=4, R=38 (config 2: 150-bp reads on four lanes), 2 steps per trip = 76 cells per lane", ["-DGG=4", "-DRR=38", "-DFORM_=2", "-DMINB=8"])
+    loop_listing(out, "ug_g8r19", "Uniform-GCP form, G=8, R=19 (150-bp reads with per-position indel qualities: config 4, PCR-model HaplotypeCaller), 4 steps per trip = 76 cells per lane",
+                 ["-DGG=8", "-DRR=19", "-DFORM_=1", "-DMINB=12"])
+    loop_listing(out, "f64u_g16r10", "FP64 rerun, uniform-GCP form, G=16, R=10 (250-bp reads of config 5), queue kernel", ["-DGG=16", "-DRR=10", "-DFORM_=1", "-DMINB=12", "-DTT=double", "-DQUEUE_KERNEL"])
+    open(os.path.join(ROOT, "profiles", "r02_sass_audit.md"), "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -146,11 +146,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("FCS_PHMM_LIB", LIB_PATH)  # developer knob: A/B builds of the same library (tools/gpu/*.sh)
+    if not os.path.exists(path):
         raise OSError(
-            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+            f"{path} is missing: build it with `python __graft_entry__.py build` "
             "(nvcc, sm_100a).  There is no CPU or pure-Python fallback for the PairHMM path.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the ABI and the binding drift apart
         fn.restype = res

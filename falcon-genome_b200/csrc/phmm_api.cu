@@ -34,13 +34,15 @@ class RegionInput : public Input {
   double* out(int64_t g) const override { return r_[g].out_log10; }
   uint8_t* used(int64_t g) const override { return r_[g].out_used_fp64; }
   float* raw(int64_t) const override { return nullptr; }
-  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const override {
+  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh, uint32_t& max_rl) const override {
     const fcs_phmm_region& x = r_[g];
     uint64_t a = 0, b = 0;
-    for (int32_t i = 0; i < x.n_reads; ++i) a += (uint64_t)(x.reads[i].len > 0 ? x.reads[i].len : 0);
+    int32_t m = 0;
+    for (int32_t i = 0; i < x.n_reads; ++i) { const int32_t l = x.reads[i].len; a += (uint64_t)(l > 0 ? l : 0); m = l > m ? l : m; }
     for (int32_t j = 0; j < x.n_haps; ++j) b += (uint64_t)(x.haps[j].len > 0 ? x.haps[j].len : 0);
     sr = a;
     sh = b;
+    max_rl = (uint32_t)m;
   }
 
  private:

@@ -113,6 +113,9 @@ static int uniform_gcp(const uint8_t* c, int32_t len) {
 static inline void copy_padded16(uint8_t* dst, const uint8_t* src, uint32_t len, uint8_t pad) {
 #if defined(__SSE2__)
   uint32_t i = 0;
+  // (non-temporal stores were tried for the staging buffer -- it is only ever read by the DMA engine -- and lost by
+  // 10x: planes are 16-byte, not 64-byte aligned, so regular tail stores and the next plane share cache lines with
+  // the streamed ones and every write-combining buffer is flushed partially filled)
   for (; i + 16 <= len; i += 16) _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
   if (i < len) {
     // last, partly filled block: the padding first, then the final 16 source bytes on top of it (they overlap the
@@ -1446,7 +1449,7 @@ class CombinedInput : public Input {
   uint8_t* used(int64_t g) const override { const auto w = where(g); return parts_[w.first]->used(w.second); }
   float* raw(int64_t g) const override { const auto w = where(g); return parts_[w.first]->raw(w.second); }
   uint8_t* poorly(int64_t g) const override { const auto w = where(g); return parts_[w.first]->poorly(w.second); }
-  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const override { const auto w = where(g); parts_[w.first]->sum_lens(w.second, sr, sh); }
+  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh, uint32_t& max_rl) const override { const auto w = where(g); parts_[w.first]->sum_lens(w.second, sr, sh, max_rl); }
 
  private:
   std::pair<size_t, int64_t> where(int64_t g) const {
@@ -1589,12 +1592,13 @@ int Engine::compute_one(const Input& in) {
   };
   // ---- size every region once
   std::vector<uint64_t> rc_cells((size_t)n), rc_pairs((size_t)n), rc_bytes((size_t)n), rc_ub_in((size_t)n);
+  std::vector<uint32_t> rc_maxrl((size_t)n);
   auto size_range = [&](int64_t g0, int64_t g1) {
     for (int64_t g = g0; g < g1; ++g) {
       int32_t nr = 0, nh = 0;
       in.shape(g, nr, nh);
       uint64_t sr = 0, sh = 0;
-      in.sum_lens(g, sr, sh);
+      in.sum_lens(g, sr, sh, rc_maxrl[(size_t)g]);
       rc_cells[(size_t)g] = sr * sh;
       rc_pairs[(size_t)g] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
       rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
@@ -1661,6 +1665,13 @@ int Engine::compute_one(const Input& in) {
       static const int64_t cap_cells = env_i64("FCS_PHMM_CHUNK_CAP_CELLS", 3000000000LL);  // developer knob
       limit = std::min<int64_t>(cap_cells, std::max<int64_t>(500000000LL, want));
     }
+    // Chunks are cut from the device's regions in order of their longest read (descending): a chunk then holds a
+    // narrow band of read lengths, its reads share a few kernel classes, and those classes are popular enough in the
+    // chunk to keep their exact rows-per-lane (Planner: fine_len) instead of rounding up to the coarse grid.  Results
+    // are scattered by region index, so the order is free.  (Ragged calls only: equal-length regions keep their order.)
+    static const bool sort_regions = env_i64("FCS_PHMM_SORT_REGIONS", 1) != 0;  // developer knob
+    if (sort_regions && total > 2 * (uint64_t)limit && part[d].size() > 8)
+      std::stable_sort(part[d].begin(), part[d].end(), [&](int64_t a, int64_t b) { return rc_maxrl[(size_t)a] > rc_maxrl[(size_t)b]; });
     uint64_t cells = 0, pairs = 0, bytes = 0;
     std::vector<int64_t> cur;
     auto& chunks = work[d].chunks;
@@ -1845,14 +1856,16 @@ class FlatInput : public Input {
   double* out(int64_t g) const override { return out_ ? out_ + b_.reg_out0[g] : nullptr; }
   uint8_t* used(int64_t g) const override { return used_ ? used_ + b_.reg_out0[g] : nullptr; }
   float* raw(int64_t g) const override { return raw_ ? raw_ + b_.reg_out0[g] : nullptr; }
-  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const override {
+  void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh, uint32_t& max_rl) const override {
     const int32_t* rl = b_.rd_len + b_.reg_read0[g];
     const int32_t* hl = b_.hp_len + b_.reg_hap0[g];
     uint64_t a = 0, b = 0;
-    for (int32_t i = 0; i < b_.reg_nreads[g]; ++i) a += (uint64_t)(rl[i] > 0 ? rl[i] : 0);
+    int32_t m = 0;
+    for (int32_t i = 0; i < b_.reg_nreads[g]; ++i) { a += (uint64_t)(rl[i] > 0 ? rl[i] : 0); m = rl[i] > m ? rl[i] : m; }
     for (int32_t j = 0; j < b_.reg_nhaps[g]; ++j) b += (uint64_t)(hl[j] > 0 ? hl[j] : 0);
     sr = a;
     sh = b;
+    max_rl = (uint32_t)m;
   }
 
  private:

@@ -46,13 +46,14 @@ class Input {
   virtual float* raw(int64_t g) const = 0;
   // poorly-modelled flags of region g's reads (caller's read order), or null (finalize epilogue)
   virtual uint8_t* poorly(int64_t g) const { (void)g; return nullptr; }
-  // Sum of the (non-negative) read and haplotype lengths of region g: the sizing pass of a call walks every
-  // read once, so inputs override this with a loop over their own arrays (no virtual call per read).
-  virtual void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh) const {
+  // Sum of the (non-negative) read and haplotype lengths of region g and its longest read: the sizing pass of a call
+  // walks every read once, so inputs override this with a loop over their own arrays (no virtual call per read).
+  virtual void sum_lens(int64_t g, uint64_t& sr, uint64_t& sh, uint32_t& max_rl) const {
     int32_t nr = 0, nh = 0;
     shape(g, nr, nh);
     sr = sh = 0;
-    for (int32_t i = 0; i < nr; ++i) { const int32_t l = read(g, i).len; sr += (uint64_t)(l > 0 ? l : 0); }
+    max_rl = 0;
+    for (int32_t i = 0; i < nr; ++i) { const int32_t l = read(g, i).len; sr += (uint64_t)(l > 0 ? l : 0); if (l > 0 && (uint32_t)l > max_rl) max_rl = (uint32_t)l; }
     for (int32_t j = 0; j < nh; ++j) { const int32_t l = hap(g, j).len; sh += (uint64_t)(l > 0 ? l : 0); }
   }
 };

@@ -52,7 +52,10 @@ int f64_queue_count();
 int f64_queue_id(int G, int R);
 const ClassRef* f64_queue_class(int qid, int form);
 
-constexpr int kTierMinBlocks[3] = {16, 12, 8};
+#ifndef PHMM_TIER1_MINB
+#define PHMM_TIER1_MINB 12
+#endif
+constexpr int kTierMinBlocks[3] = {16, PHMM_TIER1_MINB, 8};  // (developer builds vary the middle tier: -DPHMM_TIER1_MINB=10)
 
 // striped generic kernels (phmm_generic.cuh): any read / haplotype length
 cudaError_t launch_generic_f32(const KParams& p, unsigned grid, cudaStream_t s);

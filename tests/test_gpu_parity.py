@@ -402,17 +402,50 @@ def test_finalize_epilogue_on_device(oracle):
     assert poorly.any()  # the low-quality batch has poorly modelled reads
 
 
-def test_full_size_config2_properties(hmm):
-    """BASELINE config 2 at full size (100k pairs): size-independent properties instead of the
-    oracle — every read's best haplotype scores far above a random one, results are finite, no
-    pair needs FP64, and the run is bit-reproducible."""
+def _full_size_parity(hmm, oracle, b):
+    """The parity bars at benchmark size: decisions and raw FP32 sums against the float twin (bit level), every pair
+    against the DOUBLE-precision oracle (1e-4), per-read best haplotype, bit-reproducibility."""
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    err = check_against_oracle(oracle, b, out, used, raw)      # float twin (SIMD port, IEEE subnormals) + arg-max
+    dbl = oracle.batch_double(b)                                # the north_star's reference arithmetic, every pair
+    fin = np.isfinite(dbl)
+    assert np.array_equal(fin, np.isfinite(out)) and np.abs(out[fin] - dbl[fin]).max() <= TOL
+    out2, used2 = hmm.compute_flat(b)
+    assert np.array_equal(out, out2) and np.array_equal(used, used2)
+    return out, used, err
+
+
+def test_full_size_config2(hmm, oracle):
+    """BASELINE config 2 at full size: 100 000 pairs, 150 x 300, uniform quals (the bench default)."""
     b = synth.config2_uniform()
-    out, used = hmm.compute_flat(b)
-    assert np.isfinite(out).all() and used.sum() <= 5  # reads drawn from one haplotype rarely underflow against another
-    out2, _ = hmm.compute_flat(b)
-    assert np.array_equal(out, out2)
+    out, used, _ = _full_size_parity(hmm, oracle, b)
+    assert b.n_pairs == 100_000 and used.sum() <= 5  # reads drawn from one haplotype rarely underflow against another
     m = out.reshape(100, 100, 10)
     assert (m.max(axis=2) > -45).all() and (m <= 0).all()
+
+
+def test_full_size_config3_chunk(hmm, oracle):
+    """One 2000-region chunk of the config-3 stream (405 k pairs, 24 Gcells, ragged lengths, ~9 % FP64 reruns)."""
+    b = synth.config3_wgs(n_regions=2000, seed=3003, chunk=0)
+    _, used, _ = _full_size_parity(hmm, oracle, b)
+    assert b.n_regions == 2000 and 0.02 < used.mean() < 0.3
+
+
+def test_full_size_config4_sample(hmm, oracle):
+    """Twenty Mutect2-shaped regions (415 k pairs, 17 Gcells, deep pileups, per-position indel qualities)."""
+    b = synth.config4_mutect2(n_regions=20, seed=4004)
+    _full_size_parity(hmm, oracle, b)
+
+
+def test_full_size_config5(hmm, oracle):
+    """All 20 000 pairs of the underflow stress config: nearly every pair takes the FP64 path; results against the
+    double oracle to 1e-9."""
+    b = synth.config5_underflow()
+    out, used, _ = _full_size_parity(hmm, oracle, b)
+    assert b.n_pairs == 20_000 and used.mean() > 0.9
+    dbl = oracle.batch_double(b)
+    sel = (used == 1) & np.isfinite(dbl)
+    assert np.abs(out[sel] - dbl[sel]).max() <= 1e-9
 
 
 def test_in_process_multi_gpu_dispatch(oracle):

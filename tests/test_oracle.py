@@ -213,3 +213,29 @@ def test_property_high_bits_of_qualities_and_n_wildcard(oracle, p, seed):
     k = int(rng.integers(0, len(bases)))
     with_n = bases[:k] + b"N" + bases[k + 1:]
     assert oracle.log10_double((with_n, q, i, d, c), hap) >= base - 1e-12
+
+
+def test_arithmetic_variants_bracket_the_pinned_contract(oracle):
+    """oracle/pairhmm_variants.c: variant 0 is the pinned contract (bit-identical raw sums, decisions and results);
+    every arithmetic difference a real GKL binary may have (no FMA, FTZ/DAZ, powf table, libm log10f, split last-row
+    sums, and all of them together) stays within a few float ulps of log10 L -- two orders of magnitude inside the
+    1e-4 tolerance -- and flips no float->double decision on these batches (profiles/r02_oracle_variants.md has the
+    full-size table)."""
+    from falcon_genome_b200 import synth
+
+    for b in (synth.config1_golden(n_regions=16, seed=31), synth.config5_underflow(n_regions=1, seed=32), synth.tiny_mixed(seed=33, n_regions=10)):
+        o0, u0, r0, _ = oracle.batch_variant(b, 0)
+        os_, us_, rs_, _ = oracle.batch_simd(b)
+        assert np.array_equal(r0.view(np.uint32), rs_.view(np.uint32)) and np.array_equal(u0, us_) and np.array_equal(o0, os_)
+        dbl = oracle.batch_double(b)
+        fin = np.isfinite(dbl)
+        assert np.abs(o0[fin] - dbl[fin]).max() <= 1e-4
+        for flags in (oracle.VAR_NOFMA, oracle.VAR_FTZ, oracle.VAR_POWF, oracle.VAR_LOG10F, oracle.VAR_SPLITSUM, oracle.VAR_GKL_STRICT_AVX512,
+                      oracle.VAR_GKL_STRICT_AVX):
+            o, u, r, _ = oracle.batch_variant(b, flags)
+            same = u == u0
+            ok = same & np.isfinite(o) & np.isfinite(o0)
+            assert np.abs(o[ok] - o0[ok]).max() <= 2e-5, flags
+            # a decision may only differ where the raw float sum sits within rounding distance of the threshold
+            flipped = ~same
+            assert (np.abs(r0[flipped].astype(np.float64) / 1e-28 - 1.0) < 1e-4).all(), flags

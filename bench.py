@@ -435,7 +435,7 @@ def main():
     ap.add_argument("--preheat-s", type=float, default=2.0, help="untimed pre-heat of the same kernels right before the timed steps")
     ap.add_argument("--threads", type=int, default=0,
                     help="host packing threads per rank (the library's max_threads, GATK's --native-pair-hmm-threads); "
-                         "0 = this rank's share of the host cores minus two (Python + driver threads), between 1 and 4")
+                         "0 = this rank's share of the host cores, between 1 and 4")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="how the timed steps are kept from re-using inputs out of L2: rotate over resident batches whose "
                          "total size exceeds L2 (default), or write a 192 MiB buffer between steps")
@@ -504,13 +504,14 @@ def main():
         return float(t.item())
 
     batch, desc = make_workload(args.workload, rank)
-    # One rank per GPU shares the box's host cores with the other ranks.  Each rank also runs its Python main thread,
-    # the NVML sampler and the CUDA driver's own threads, so the packing threads get the rank's share of the cores
-    # minus two: more threads than cores only makes packing, event waits and the interpreter fight for the same cores
-    # (round 1: 8 ranks x 4 packing threads on 32 cores reached 0.82 of linear end to end).
+    # One rank per GPU shares the box's host cores with the other ranks: at most the rank's share of the cores, and at
+    # most the library default of 4 (GATK's --native-pair-hmm-threads).  Measured on a 4-core affinity mask (what a
+    # rank gets on an 8-GPU / 32-core box), config 2 end to end: 1 / 2 / 3 / 4 packing threads = 2579 / 2971 / 3262 / 3411
+    # GCUPS -- the calling thread is one of the packers and the sampler sleeps, so four threads on four cores do not
+    # oversubscribe; with fewer cores the library keeps the same chunk schedule and lets fewer threads pull from it.
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     share = host_threads() // max(1, local_world)
-    pack_threads = args.threads if args.threads > 0 else max(1, min(4, share - 2 if local_world > 1 else share))
+    pack_threads = args.threads if args.threads > 0 else max(1, min(4, share))
     hmm = PairHMM(devices=[dev_index], max_threads=pack_threads)
     res = [hmm.resident(batch, 0)]
     launches_per_step = res[0].launches

@@ -1654,11 +1654,17 @@ int Engine::compute_one(const Input& in) {
   for (size_t d = 0; d < D; ++d) {
     uint64_t total = 0;
     for (int64_t g : part[d]) total += rc_cells[(size_t)g];
+    // The chunk schedule (sizes, ramp) is laid out for at least four packing threads even when the handle has fewer:
+    // how finely a call is pipelined against the device should not depend on how many cores the process was given
+    // (measured on a 4-core mask, config 2: 1 / 2 / 3 / 4 threads with their own schedules 2579 / 2971 / 3262 / 3411 GCUPS
+    // end to end, the host work itself being ~0.9 ms of one core per 1.3 ms call).
+    static const int min_sched = (int)std::max<int64_t>(1, env_i64("FCS_PHMM_SCHED_THREADS", 4));  // developer knob
+    const int sched_threads = std::max(pack_threads_, min_sched);
     int64_t limit = max_chunk_cells_;
     const bool ramp = limit <= 0;
     if (limit <= 0) {
       static const int64_t cpt_x10 = env_i64("FCS_PHMM_CHUNKS_PER_THREAD_X10", 20);  // developer knob
-      const int64_t want = (int64_t)(total * 10 / (uint64_t)(cpt_x10 * std::max(1, pack_threads_)));
+      const int64_t want = (int64_t)(total * 10 / (uint64_t)(cpt_x10 * sched_threads));
       // at most ~3 Gcells (about 1 ms of device work, 8+ waves of CTAs): larger chunks gain nothing on the device, and
       // a batch that merges several callers would otherwise grow every slot's pinned staging to a multiple of what
       // a single call needs (re-allocating pinned memory costs milliseconds per slot)
@@ -1682,7 +1688,7 @@ int Engine::compute_one(const Input& in) {
       // ramp: the first round of chunks (one per packing thread) is small so that the device starts after a fraction of
       // a millisecond of planning + packing, later rounds double.  Style 2 adds a round at 1/16 for calls whose regular
       // chunk is large (config 3: 3 Gcells = 1.1 ms of host work before the first launch otherwise).
-      const int round = (int)chunks.size() / std::max(1, pack_threads_);
+      const int round = (int)chunks.size() / sched_threads;
       if (ramp && ramp_style == 2 && limit >= 1500000000LL) {
         if (round == 0) lim_now = std::max<int64_t>(limit / 16, 125000000LL);
         else if (round == 1) lim_now = std::max<int64_t>(limit / 4, 125000000LL);

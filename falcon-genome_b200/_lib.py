@@ -114,12 +114,20 @@ SIGNATURES = {
 
 # libfcs_pairhmm_client.so (no CUDA): client of the fcs-pairhmm-nam daemon
 CLIENT_LIB_PATH = os.path.join(_HERE, "libfcs_pairhmm_client.so")
+class RemoteViews(C.Structure):
+    _fields_ = [("read_bases", u8p), ("read_q", u8p), ("read_i", u8p), ("read_d", u8p), ("read_c", u8p), ("rd_off", i64p), ("rd_len", i32p),
+                ("hap_bases", u8p), ("hp_off", i64p), ("hp_len", i32p), ("reg_read0", i32p), ("reg_nreads", i32p), ("reg_hap0", i32p),
+                ("reg_nhaps", i32p), ("out_log10", f64p), ("out_used_fp64", u8p)]
+
+
 CLIENT_SIGNATURES = {
     "fcs_pairhmm_remote_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "fcs_pairhmm_remote_compute_flat": (C.c_int, [C.c_void_p, C.POINTER(FlatStruct), f64p, u8p]),
     "fcs_pairhmm_remote_last_error": (C.c_char_p, [C.c_void_p]),
     "fcs_pairhmm_remote_close": (None, [C.c_void_p]),
     "fcs_pairhmm_remote_uses_shm": (C.c_int, [C.c_void_p]),
+    "fcs_pairhmm_remote_reserve": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(RemoteViews)]),
+    "fcs_pairhmm_remote_compute_reserved": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

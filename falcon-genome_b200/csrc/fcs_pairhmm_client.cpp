@@ -36,6 +36,8 @@ struct fcs_phmm_remote {
   bool shm = true;          // shared-memory transport (phmm_shm.h); false: byte-stream protocol
   uint8_t* seg = nullptr;   // this connection's segment, mapped here and in the daemon
   size_t seg_bytes = 0;
+  uint64_t reserved_pairs = 0;  // fcs_pairhmm_remote_reserve: a batch is being built in the segment
+  bool reserved = false;
 };
 static thread_local std::string g_cerr;
 
@@ -137,6 +139,66 @@ static bool ensure_segment(fcs_phmm_remote* r, size_t need, bool& conn_lost) {
   return true;
 }
 
+// Section offsets of a batch of the given shape (phmm_shm.h); returns the segment bytes it needs.
+static uint64_t layout_segment(ShmHeader& h, int64_t n_regions, uint64_t n_reads, uint64_t n_haps, uint64_t read_bytes, uint64_t hap_bytes,
+                               uint64_t pairs) {
+  std::memset(&h, 0, sizeof(h));
+  h.magic = fcsphmm::kShmMagic;
+  h.version = fcsphmm::kShmVersion;
+  h.n_regions = n_regions;
+  h.n_reads = (int64_t)n_reads;
+  h.n_haps = (int64_t)n_haps;
+  h.n_pairs = pairs;
+  h.read_bytes = read_bytes;
+  h.hap_bytes = hap_bytes;
+  uint64_t off = shm_align(sizeof(ShmHeader));
+  auto section = [&](uint64_t bytes) { const uint64_t o = off; off = shm_align(off + bytes); return o; };
+  h.off_read_bases = section(read_bytes);
+  h.off_read_q = section(read_bytes);
+  h.off_read_i = section(read_bytes);
+  h.off_read_d = section(read_bytes);
+  h.off_read_c = section(read_bytes);
+  h.off_rd_off = section(n_reads * 8);
+  h.off_rd_len = section(n_reads * 4);
+  h.off_hap_bases = section(hap_bytes);
+  h.off_hp_off = section(n_haps * 8);
+  h.off_hp_len = section(n_haps * 4);
+  h.off_reg_read0 = section((uint64_t)n_regions * 4);
+  h.off_reg_nreads = section((uint64_t)n_regions * 4);
+  h.off_reg_hap0 = section((uint64_t)n_regions * 4);
+  h.off_reg_nhaps = section((uint64_t)n_regions * 4);
+  h.off_out = section(pairs * 8);
+  h.off_used = section(pairs);
+  h.total_bytes = off;
+  return off;
+}
+
+// Doorbell + reply for the batch described at offset 0 of the segment.  Returns the call's result code.
+static int ring_segment(fcs_phmm_remote* r, uint64_t pairs) {
+  uint8_t bell[12];
+  const uint32_t tag = fcsphmm::kShmRequest;
+  const uint64_t zero = 0;
+  std::memcpy(bell, &tag, 4);
+  std::memcpy(bell + 4, &zero, 8);
+  int32_t rc = 0;
+  uint64_t n = 0;
+  if (!wr(r->fd, bell, sizeof(bell)) || !read_reply(r, rc, n)) {
+    r->err = "connection to the PairHMM daemon lost";
+    return FCS_PHMM_ENODEV;
+  }
+  if (rc != FCS_PHMM_OK) {
+    std::string msg((size_t)n, '\0');
+    if (n) rd(r->fd, &msg[0], (size_t)n);
+    r->err = "daemon: " + msg;
+    return rc;
+  }
+  if (n != pairs) {
+    r->err = "daemon returned an unexpected number of pairs";
+    return FCS_PHMM_EINVAL;
+  }
+  return FCS_PHMM_OK;
+}
+
 // 0 = done through the segment (rc in `result`), 1 = not possible, use the byte stream.
 static int compute_via_shm(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64, int& result) {
   uint64_t n_reads = 0, n_haps = 0, pairs = 0, read_bytes = 0, hap_bytes = 0;
@@ -164,34 +226,7 @@ static int compute_via_shm(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, dou
   }
   if (n_reads > 0x7fffffffULL || n_haps > 0x7fffffffULL) return 1;
   ShmHeader h;
-  std::memset(&h, 0, sizeof(h));
-  h.magic = fcsphmm::kShmMagic;
-  h.version = fcsphmm::kShmVersion;
-  h.n_regions = b->n_regions;
-  h.n_reads = (int64_t)n_reads;
-  h.n_haps = (int64_t)n_haps;
-  h.n_pairs = pairs;
-  h.read_bytes = read_bytes;
-  h.hap_bytes = hap_bytes;
-  uint64_t off = shm_align(sizeof(ShmHeader));
-  auto section = [&](uint64_t bytes) { const uint64_t o = off; off = shm_align(off + bytes); return o; };
-  h.off_read_bases = section(read_bytes);
-  h.off_read_q = section(read_bytes);
-  h.off_read_i = section(read_bytes);
-  h.off_read_d = section(read_bytes);
-  h.off_read_c = section(read_bytes);
-  h.off_rd_off = section(n_reads * 8);
-  h.off_rd_len = section(n_reads * 4);
-  h.off_hap_bases = section(hap_bytes);
-  h.off_hp_off = section(n_haps * 8);
-  h.off_hp_len = section(n_haps * 4);
-  h.off_reg_read0 = section((uint64_t)b->n_regions * 4);
-  h.off_reg_nreads = section((uint64_t)b->n_regions * 4);
-  h.off_reg_hap0 = section((uint64_t)b->n_regions * 4);
-  h.off_reg_nhaps = section((uint64_t)b->n_regions * 4);
-  h.off_out = section(pairs * 8);
-  h.off_used = section(pairs);
-  h.total_bytes = off;
+  const uint64_t off = layout_segment(h, b->n_regions, n_reads, n_haps, read_bytes, hap_bytes, pairs);
   bool lost = false;
   if (!ensure_segment(r, (size_t)off, lost)) {
     if (lost) { result = FCS_PHMM_ENODEV; return 0; }
@@ -235,30 +270,9 @@ static int compute_via_shm(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, dou
     }
   }
   std::memcpy(s, &h, sizeof(h));
-  uint8_t bell[12];
-  const uint32_t tag = fcsphmm::kShmRequest;
-  const uint64_t zero = 0;
-  std::memcpy(bell, &tag, 4);
-  std::memcpy(bell + 4, &zero, 8);
-  int32_t rc = 0;
-  uint64_t n = 0;
-  if (!wr(r->fd, bell, sizeof(bell)) || !read_reply(r, rc, n)) {
-    r->err = "connection to the PairHMM daemon lost";
-    result = FCS_PHMM_ENODEV;
-    return 0;
-  }
-  if (rc != FCS_PHMM_OK) {
-    std::string msg((size_t)n, '\0');
-    if (n) rd(r->fd, &msg[0], (size_t)n);
-    r->err = "daemon: " + msg;
-    result = rc;
-    return 0;
-  }
-  if (n != pairs) {
-    r->err = "daemon returned an unexpected number of pairs";
-    result = FCS_PHMM_EINVAL;
-    return 0;
-  }
+  r->reserved = false;
+  result = ring_segment(r, pairs);
+  if (result != FCS_PHMM_OK) return 0;
   std::memcpy(out, s + h.off_out, (size_t)pairs * sizeof(double));
   if (used_fp64) std::memcpy(used_fp64, s + h.off_used, (size_t)pairs);
   result = FCS_PHMM_OK;
@@ -298,6 +312,54 @@ FCS_PHMM_API void fcs_pairhmm_remote_close(fcs_phmm_remote* r) {
 FCS_PHMM_API int fcs_pairhmm_remote_uses_shm(const fcs_phmm_remote* r) { return r && r->shm ? 1 : 0; }
 
 FCS_PHMM_API const char* fcs_pairhmm_remote_last_error(const fcs_phmm_remote* r) { return r ? r->err.c_str() : g_cerr.c_str(); }
+
+// Build the batch IN the segment: reserve() lays out a batch of the announced shape in this connection's segment
+// and hands out writable views; the caller fills them (a JNI shim: GetByteArrayRegion straight into the planes --
+// the one copy that leaves the JVM) and compute_reserved() rings the daemon; the results stay in the segment
+// (views.out_log10 / out_used_fp64) until the next reserve or compute call on this connection.
+FCS_PHMM_API int fcs_pairhmm_remote_reserve(fcs_phmm_remote* r, int64_t n_regions, int64_t n_reads, int64_t n_haps, uint64_t read_bytes,
+                                            uint64_t hap_bytes, uint64_t n_pairs, fcs_phmm_remote_views* v) {
+  if (!r || !v || n_regions < 0 || n_reads < 0 || n_haps < 0) return FCS_PHMM_EINVAL;
+  r->reserved = false;
+  if (!r->shm) {
+    r->err = "in-segment batches need the shared-memory transport (FCS_PHMM_REMOTE_SHM=0 or the daemon declined the segment)";
+    return FCS_PHMM_EUNSUPPORTED;
+  }
+  if ((uint64_t)n_reads > 0x7fffffffULL || (uint64_t)n_haps > 0x7fffffffULL || n_pairs > 0x7fffffffULL) {
+    r->err = "batch too large for one call";
+    return FCS_PHMM_EUNSUPPORTED;
+  }
+  ShmHeader h;
+  const uint64_t need = layout_segment(h, n_regions, (uint64_t)n_reads, (uint64_t)n_haps, read_bytes, hap_bytes, n_pairs);
+  bool lost = false;
+  if (!ensure_segment(r, (size_t)need, lost)) {
+    if (!lost) r->err = "the shared segment could not be set up";
+    return lost ? FCS_PHMM_ENODEV : FCS_PHMM_EUNSUPPORTED;
+  }
+  uint8_t* s = r->seg;
+  std::memcpy(s, &h, sizeof(h));
+  v->read_bases = s + h.off_read_bases; v->read_q = s + h.off_read_q; v->read_i = s + h.off_read_i;
+  v->read_d = s + h.off_read_d; v->read_c = s + h.off_read_c;
+  v->rd_off = reinterpret_cast<int64_t*>(s + h.off_rd_off); v->rd_len = reinterpret_cast<int32_t*>(s + h.off_rd_len);
+  v->hap_bases = s + h.off_hap_bases;
+  v->hp_off = reinterpret_cast<int64_t*>(s + h.off_hp_off); v->hp_len = reinterpret_cast<int32_t*>(s + h.off_hp_len);
+  v->reg_read0 = reinterpret_cast<int32_t*>(s + h.off_reg_read0); v->reg_nreads = reinterpret_cast<int32_t*>(s + h.off_reg_nreads);
+  v->reg_hap0 = reinterpret_cast<int32_t*>(s + h.off_reg_hap0); v->reg_nhaps = reinterpret_cast<int32_t*>(s + h.off_reg_nhaps);
+  v->out_log10 = reinterpret_cast<const double*>(s + h.off_out);
+  v->out_used_fp64 = s + h.off_used;
+  r->reserved = true;
+  r->reserved_pairs = n_pairs;
+  return FCS_PHMM_OK;
+}
+
+FCS_PHMM_API int fcs_pairhmm_remote_compute_reserved(fcs_phmm_remote* r) {
+  if (!r) return FCS_PHMM_EINVAL;
+  if (!r->reserved) {
+    r->err = "no batch reserved on this connection";
+    return FCS_PHMM_EINVAL;
+  }
+  return ring_segment(r, r->reserved_pairs);  // (the reservation stays valid: the same batch may be filled again)
+}
 
 // Same contract as fcs_pairhmm_compute_flat, executed by the daemon.
 FCS_PHMM_API int fcs_pairhmm_remote_compute_flat(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64) {

@@ -38,6 +38,44 @@ class RemotePairHMM:
             raise PairHMMError(rc, (self._lib.fcs_pairhmm_remote_last_error(self._h) or b"").decode())
         return out, used
 
+    def compute_in_segment(self, b: FlatBatch):
+        """The zero-copy path (``fcs_pairhmm_remote_reserve`` / ``compute_reserved``): the batch is written straight
+        into the connection's shared segment through the views the client hands out (here with numpy; a JNI shim would
+        GetByteArrayRegion into them), the results are read in place.  Needs a dense FlatBatch (regions in order)."""
+        v = _lib.RemoteViews()
+        nr, nh, ng = b.n_reads, b.n_haps, b.n_regions
+        rbytes, hbytes = int(b.rd_len.astype(np.int64).sum()), int(b.hp_len.astype(np.int64).sum())
+        rc = self._lib.fcs_pairhmm_remote_reserve(self._h, ng, nr, nh, rbytes, hbytes, b.n_pairs, C.byref(v))
+        if rc != _lib.OK:
+            raise PairHMMError(rc, (self._lib.fcs_pairhmm_remote_last_error(self._h) or b"").decode())
+
+        def view(ptr, n, dtype):
+            return np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n] if n else np.zeros(0, dtype)
+
+        # densely re-indexed planes (reads / haplotypes in region order), written in place
+        rd_off = (np.cumsum(b.rd_len.astype(np.int64)) - b.rd_len).astype(np.int64)
+        hp_off = (np.cumsum(b.hp_len.astype(np.int64)) - b.hp_len).astype(np.int64)
+        for name, src in (("read_bases", b.read_bases), ("read_q", b.read_q), ("read_i", b.read_i), ("read_d", b.read_d), ("read_c", b.read_c)):
+            dst = view(getattr(v, name), rbytes, np.uint8)
+            for k in range(nr):
+                dst[rd_off[k]:rd_off[k] + b.rd_len[k]] = src[b.rd_off[k]:b.rd_off[k] + b.rd_len[k]]
+        dst = view(v.hap_bases, hbytes, np.uint8)
+        for k in range(nh):
+            dst[hp_off[k]:hp_off[k] + b.hp_len[k]] = b.hap_bases[b.hp_off[k]:b.hp_off[k] + b.hp_len[k]]
+        view(v.rd_off, nr, np.int64)[:] = rd_off
+        view(v.rd_len, nr, np.int32)[:] = b.rd_len
+        view(v.hp_off, nh, np.int64)[:] = hp_off
+        view(v.hp_len, nh, np.int32)[:] = b.hp_len
+        view(v.reg_read0, ng, np.int32)[:] = b.reg_read0
+        view(v.reg_nreads, ng, np.int32)[:] = b.reg_nreads
+        view(v.reg_hap0, ng, np.int32)[:] = b.reg_hap0
+        view(v.reg_nhaps, ng, np.int32)[:] = b.reg_nhaps
+        rc = self._lib.fcs_pairhmm_remote_compute_reserved(self._h)
+        if rc != _lib.OK:
+            raise PairHMMError(rc, (self._lib.fcs_pairhmm_remote_last_error(self._h) or b"").decode())
+        n = b.n_pairs
+        return view(v.out_log10, n, np.float64).copy(), view(v.out_used_fp64, n, np.uint8).copy()
+
     @property
     def uses_shm(self) -> bool:
         """True while requests go through the shared-memory segment, False on the byte-stream protocol."""

@@ -242,6 +242,26 @@ FCS_PHMM_API int fcs_pairhmm_remote_open(const char* socket_path, fcs_phmm_remot
 FCS_PHMM_API int fcs_pairhmm_remote_compute_flat(fcs_phmm_remote* r, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64);
 FCS_PHMM_API const char* fcs_pairhmm_remote_last_error(const fcs_phmm_remote* r);
 FCS_PHMM_API void fcs_pairhmm_remote_close(fcs_phmm_remote* r);
+/* Zero-copy variant: build the batch IN the connection's segment.  reserve() lays out a batch of the announced shape
+ * (read_bytes = bytes of each of the five read planes, hap_bytes = haplotype bytes, n_pairs = sum over regions of
+ * reads x haplotypes; reads and haplotypes indexed densely in region order) and hands out writable views; the caller
+ * fills every array, then compute_reserved() rings the daemon.  Results are read in place (out_log10[reg_out0 + r*nh + h]
+ * with reg_out0 the running sum of pairs) and stay valid until the next reserve / compute call on the connection.
+ * This is what the JNI shim of a JVM behind the daemon does: GetByteArrayRegion straight into the planes. */
+typedef struct {
+  uint8_t *read_bases, *read_q, *read_i, *read_d, *read_c;
+  int64_t* rd_off;
+  int32_t* rd_len;
+  uint8_t* hap_bases;
+  int64_t* hp_off;
+  int32_t* hp_len;
+  int32_t *reg_read0, *reg_nreads, *reg_hap0, *reg_nhaps;
+  const double* out_log10;
+  const uint8_t* out_used_fp64;
+} fcs_phmm_remote_views;
+FCS_PHMM_API int fcs_pairhmm_remote_reserve(fcs_phmm_remote* r, int64_t n_regions, int64_t n_reads, int64_t n_haps, uint64_t read_bytes,
+                                            uint64_t hap_bytes, uint64_t n_pairs, fcs_phmm_remote_views* views);
+FCS_PHMM_API int fcs_pairhmm_remote_compute_reserved(fcs_phmm_remote* r);
 /* 1 while requests travel through the connection's shared-memory segment (the default; the batch is written
  * once into a sealed memfd that the daemon maps, csrc/phmm_shm.h), 0 on the byte-stream protocol
  * (FCS_PHMM_REMOTE_SHM=0, or a daemon that declined the segment). */

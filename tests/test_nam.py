@@ -54,6 +54,24 @@ def test_daemon_serves_clients_and_stops_on_sigalrm(tmp_path, hmm):
 
 
 @pytest.mark.gpu
+def test_client_builds_the_batch_in_the_segment(tmp_path, hmm):
+    """fcs_pairhmm_remote_reserve / compute_reserved: the batch is written in place into the connection's segment (no
+    client-side staging copy), the results are read in place; same bits as the in-process library, also after the
+    segment had to grow and when the reservation is refilled."""
+    sock = str(tmp_path / "nam.sock")
+    small, big = synth.tiny_mixed(seed=75, n_regions=5), synth.config1_golden(n_regions=30, seed=76)
+    with NamDaemon(sock, devices=1):
+        with RemotePairHMM(sock) as c:
+            for b in (small, big, small):
+                ref, uref = hmm.compute_flat(b)
+                out, used = c.compute_in_segment(b)
+                assert np.array_equal(out, ref) and np.array_equal(used, uref)
+            o2, u2 = c.compute_flat(big)  # the copying call still works on the same connection
+            rb, ub = hmm.compute_flat(big)
+            assert np.array_equal(o2, rb) and np.array_equal(u2, ub)
+
+
+@pytest.mark.gpu
 def test_byte_stream_transport_gives_the_same_results(tmp_path, hmm, monkeypatch):
     sock = str(tmp_path / "nam.sock")
     b = synth.tiny_mixed(seed=74, n_regions=5)

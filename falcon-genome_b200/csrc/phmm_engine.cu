@@ -60,12 +60,12 @@ static int64_t env_i64(const char* name, int64_t dflt) {
 }
 
 // class lookup by read length (hot in the planner: one lookup per read)
-static std::vector<const ClassRef*> g_f32_by_len[3];  // [form]
-static std::vector<const ClassRef*> g_f32_coarse_by_len[3];
+static std::vector<const ClassRef*> g_f32_by_len[4];  // [form]
+static std::vector<const ClassRef*> g_f32_coarse_by_len[4];
 static std::vector<int16_t> g_qid_by_len;             // FP64 queue id
 static std::once_flag g_cls_once;
 static void build_len_tables() {
-  for (int form = 0; form < 3; ++form) {
+  for (int form = 0; form < 4; ++form) {
     g_f32_by_len[form].assign(1025, nullptr);
     for (int len = 1; len <= 1024; ++len) g_f32_by_len[form][len] = select_class(false, form, len);
     g_f32_coarse_by_len[form].assign(1025, nullptr);
@@ -475,6 +475,7 @@ struct Planner {
     for (auto& b : s.buckets) { b.tasks.clear(); b.hs = 0; b.stage = 0; b.cls_mask = 0; }
     s.order.clear();
     s.ukeys.clear();
+    s.rlayout.clear();
     s.genlist.clear();
     s.gen_flags.clear();
     uint32_t gen64_cap = 0, gen_maxlh = 0;
@@ -516,6 +517,7 @@ struct Planner {
     // of the chunk: a thin extra launch spread over many (G, R) classes next to the main one costs more
     // (instruction cache, 8-CTA/SM footprint) than its faster loop gains (measured on config 3: -7 %).
     std::vector<int> all_gcp, all_ukey;
+    std::vector<uint32_t> all_layout;  // blob layout flags per read (phmm_types.h read_layout)
     bool ua_chunk = false;
     // reads per fine class (keyed by the general-form class of the length: the forms share the (G, R) grid
     // closely enough for a popularity test)
@@ -542,6 +544,14 @@ struct Planner {
           }
           all_gcp.push_back(gq);
           all_ukey.push_back(uk);
+          // compact blob layouts: constant qualities travel in a 16-byte trailer, a deletion plane equal to the insertion
+          // plane (GATK writes both from one value) is not copied at all
+          uint32_t lay = 0;
+          if (two_plane_enabled() && gq >= 0) {
+            if (uk >= 0) lay = kTwoPlaneBit;
+            else lay = kNoGcpPlaneBit | (std::memcmp(r.i, r.d, (size_t)r.len) == 0 ? kSameIndelBit : 0u);
+          }
+          all_layout.push_back(lay);
           n_elig += uk >= 0;
           if (r.len >= 1 && r.len <= 1024) ++len_hist[(size_t)r.len];
         }
@@ -582,6 +592,7 @@ struct Planner {
     const uint64_t wave_pairs = (uint64_t)sm_count * 64u;
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps, ukeys;
+    std::vector<uint32_t> layouts;
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
     int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
     size_t reads_bytes = 0, haps_bytes = 0;
@@ -602,6 +613,7 @@ struct Planner {
       lens.resize(nr);
       gcps.resize(nr);
       ukeys.resize(nr);
+      layouts.resize(nr);
       hlens.resize(nh);
       uint64_t sum_r = 0, sum_h = 0;
       size_t rb = 0, hb = 0;
@@ -614,8 +626,9 @@ struct Planner {
         lens[i] = (uint32_t)r.len;
         gcps[i] = all_gcp[qual_off[k] + (size_t)i];
         ukeys[i] = all_ukey[qual_off[k] + (size_t)i];
+        layouts[i] = all_layout[qual_off[k] + (size_t)i];
         sum_r += (uint64_t)r.len;
-        rb += read_blob_bytes((uint32_t)r.len, two_plane_enabled() && ukeys[i] >= 0);
+        rb += read_blob_bytes((uint32_t)r.len, layouts[i]);
       }
       for (int32_t j = 0; j < nh; ++j) {
         const InHap h = in.hap(g, j);
@@ -712,42 +725,72 @@ struct Planner {
             if (ukeys[ord[i + x]] != ukeys[ord[i]]) ku = nullptr;
         }
         if (ku) k0 = ku;
-        const int NG = 32 / k0->G;
-        const int cnt = std::min<int32_t>(NG, nr - i);
-        int tg = gcps[ord[i]];  // uniform-GCP form only if every read of the task shares the value
-        for (int32_t x = 1; x < cnt; ++x)
-          if (gcps[ord[i + x]] != tg) tg = -1;
-        const ClassRef* kc = ku ? ku : ((tg >= 0 && k0->twin) ? k0->twin : k0);
-        if (ku) tg = ukeys[ord[i]];
-        TaskBucket* bk = nullptr;
-        for (auto& b : s.buckets)
-          if (b.tk == kc->tk && b.gcp == tg) { bk = &b; break; }
-        if (!bk) {
-          s.buckets.emplace_back();
-          bk = &s.buckets.back();
-          bk->tk = kc->tk;
-          bk->gcp = tg;
+        // Haplotype-pair form: reads with one gap-continuation quality against two haplotypes at a time in packed
+        // f32x2 arithmetic.  Throughput policy only; an odd haplotype is left to the scalar uniform-GCP class.
+        static const bool pairs_enabled = env_i64("FCS_PHMM_NO_PAIRS", 0) == 0;  // developer knob
+        const ClassRef* kp = nullptr;
+        if (!ku && !wide_G && pairs_enabled && nh >= 2 && gcps[ord[i]] >= 0) {
+          kp = fine0 ? f32_class_of_len(3, len0) : f32_coarse_class_of_len(3, len0);
+          if (kp && nr - i < 32 / kp->G) kp = select_class_for(false, 3, len0, nr - i, (int)(sum_h / (uint64_t)nh), !fine0);
+          const int cp = kp ? std::min<int32_t>(32 / kp->G, nr - i) : 0;
+          for (int32_t x = 1; kp && x < cp; ++x)
+            if (gcps[ord[i + x]] != gcps[ord[i]]) kp = nullptr;
         }
-        for (int32_t j = 0; j < nh;) {
-          uint32_t cols = 0, stage = 0;
-          int32_t j1 = j;
-          while (j1 < nh && (j1 == j || cols + hlens[j1] + (uint32_t)(kc->G - 1) <= cols_limit) && (j1 - j) < 0xffff) {
-            cols += hlens[j1] + (kc->G - 1);
-            stage += round_up16(hlens[j1]);
-            ++j1;
+        const int NG = 32 / (kp ? kp->G : k0->G);
+        const int cnt = std::min<int32_t>(NG, nr - i);
+        // tasks of reads [i + r0, i + r0 + rc) x haplotypes [j0, j1) for class kc (pairs: two haplotypes per wavefront step)
+        auto emit = [&](const ClassRef* kc, int tg, int32_t r0, int32_t rc, int32_t j0, int32_t j1, bool pairs) {
+          TaskBucket* bk = nullptr;
+          for (auto& b : s.buckets)
+            if (b.tk == kc->tk && b.gcp == tg) { bk = &b; break; }
+          if (!bk) {
+            s.buckets.emplace_back();
+            bk = &s.buckets.back();
+            bk->tk = kc->tk;
+            bk->gcp = tg;
           }
-          cols += (kc->G - 1);
-          Task t;
-          t.read0 = read_base + (uint32_t)i;
-          t.hap0 = hap_base + (uint32_t)j;
-          t.n_reads = (uint16_t)cnt;
-          t.n_haps = (uint16_t)(j1 - j);
-          t.cls = (uint32_t)kc->cls;
-          bk->tasks.push_back(t);
-          bk->hs = std::max(bk->hs, cols);
-          bk->stage = std::max(bk->stage, stage);
-          bk->cls_mask |= 1ull << kc->cls;
-          j = j1;
+          const int32_t hstep = pairs ? 2 : 1;
+          for (int32_t j = j0; j < j1;) {
+            uint32_t cols = 0, stage = 0;
+            int32_t jn = j;
+            while (jn < j1 && (jn - j) < 0xfffe) {
+              const uint32_t w = (pairs && jn + 1 < j1) ? std::max(hlens[jn], hlens[jn + 1]) : hlens[jn];
+              if (jn != j && cols + w + (uint32_t)(kc->G - 1) > cols_limit) break;
+              cols += w + (uint32_t)(kc->G - 1);
+              for (int32_t q = jn; q < std::min(jn + hstep, j1); ++q) stage += round_up16(hlens[q]);
+              jn = std::min(jn + hstep, j1);
+            }
+            cols += (uint32_t)(kc->G - 1);
+            Task t;
+            t.read0 = read_base + (uint32_t)(i + r0);
+            t.hap0 = hap_base + (uint32_t)j;
+            t.n_reads = (uint16_t)rc;
+            t.n_haps = (uint16_t)(jn - j);
+            t.cls = (uint32_t)kc->cls;
+            bk->tasks.push_back(t);
+            bk->hs = std::max(bk->hs, pairs ? 2u * cols : cols);  // in 16-bit units: a pair entry holds two table offsets
+            bk->stage = std::max(bk->stage, stage);
+            bk->cls_mask |= 1ull << kc->cls;
+            j = jn;
+          }
+        };
+        if (kp) {
+          const int tg = gcps[ord[i]];
+          const int32_t n_even = nh & ~1;
+          emit(kp, tg, 0, cnt, 0, n_even, true);
+          if (nh & 1) {
+            // the odd haplotype: scalar uniform-GCP class of the longest read, as many tasks as its lane groups need
+            const ClassRef* ks = (k0->twin && k0->tk->form == 0) ? k0->twin : k0;
+            const int ngs = 32 / ks->G;
+            for (int32_t r0 = 0; r0 < cnt; r0 += ngs) emit(ks, ks->tk->form ? tg : -1, r0, std::min<int32_t>(ngs, cnt - r0), nh - 1, nh, false);
+          }
+        } else {
+          int tg = gcps[ord[i]];  // uniform-GCP form only if every read of the task shares the value
+          for (int32_t x = 1; x < cnt; ++x)
+            if (gcps[ord[i + x]] != tg) tg = -1;
+          const ClassRef* kc = ku ? ku : ((tg >= 0 && k0->twin) ? k0->twin : k0);
+          if (ku) tg = ukeys[ord[i]];
+          emit(kc, tg, 0, cnt, 0, nh, false);
         }
         i += cnt;
       }
@@ -766,6 +809,7 @@ struct Planner {
       }
       hap_len_chunk.insert(hap_len_chunk.end(), hlens.begin(), hlens.end());
       s.ukeys.insert(s.ukeys.end(), ukeys.begin(), ukeys.begin() + nr);
+      s.rlayout.insert(s.rlayout.end(), layouts.begin(), layouts.begin() + nr);
       P.regions.push_back(g);
       P.reg_out0.push_back(P.n_pairs);
       P.n_reads += nr;
@@ -842,7 +886,12 @@ struct Planner {
           const Task& x = b.tasks[t];
           const ClassDesc& cd = b.tk->classes[x.cls];
           uint32_t cols = 0;
-          for (uint32_t j = 0; j < x.n_haps; ++j) cols += hap_len_chunk[x.hap0 + j] + (uint32_t)cd.G - 1u;
+          if (b.tk->form == 3) {
+            for (uint32_t j = 0; j < x.n_haps; j += 2)
+              cols += std::max(hap_len_chunk[x.hap0 + j], j + 1 < x.n_haps ? hap_len_chunk[x.hap0 + j + 1] : 0u) + (uint32_t)cd.G - 1u;
+          } else {
+            for (uint32_t j = 0; j < x.n_haps; ++j) cols += hap_len_chunk[x.hap0 + j] + (uint32_t)cd.G - 1u;
+          }
           cost[t] = (uint32_t)cd.R * cols;
           b.max_task_cost = std::max(b.max_task_cost, cost[t]);
         }
@@ -1017,16 +1066,17 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
       const uint32_t lp = round_up16((uint32_t)r.len);
       uint8_t* dst = base + P.off_reads + rpos;
       const uint8_t* src[5] = {r.b, r.q, r.i, r.d, r.c};
-      // constant insertion / deletion / continuation qualities (the planner's scan): two planes + a 16-byte trailer
-      const int ukey = s.ukeys[opos + oi];
-      const bool two_plane = two_plane_enabled() && ukey >= 0;
-      for (int pl = 0; pl < (two_plane ? 2 : 5); ++pl) copy_padded16(dst + (size_t)pl * lp, src[pl], (uint32_t)r.len, 0);
-      if (two_plane) {
-        uint8_t* tr = dst + 2 * (size_t)lp;
+      // blob layout from the planner's scan: constant qualities go to a 16-byte trailer, a deletion plane that equals the
+      // insertion plane is not copied
+      const uint32_t layout = s.rlayout[opos + oi];
+      const uint32_t npl = read_planes(layout);
+      for (uint32_t pl = 0; pl < npl; ++pl) copy_padded16(dst + (size_t)pl * lp, src[pl], (uint32_t)r.len, 0);
+      if (layout) {
+        uint8_t* tr = dst + (size_t)npl * lp;
         std::memset(tr, 0, 16);
-        tr[0] = (uint8_t)((ukey >> 8) & 127);   // insertion
-        tr[1] = (uint8_t)((ukey >> 16) & 127);  // deletion
-        tr[2] = (uint8_t)(ukey & 127);          // gap continuation
+        tr[0] = (uint8_t)(r.i[0] & 127);  // insertion  (read by the kernels only when the plane is absent, i.e. constant)
+        tr[1] = (uint8_t)(r.d[0] & 127);  // deletion
+        tr[2] = (uint8_t)(r.c[0] & 127);  // gap continuation
       }
       int c64 = s.gen_flags[ridx] ? kQueueGenericF64 : qid_of_len(r.len);
       if (P.latency_mode && !s.gen_flags[ridx]) {
@@ -1035,7 +1085,7 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
       }
       ReadMeta& m = rmeta[ridx];
       m.data_off16 = (uint32_t)(rpos / 16);
-      m.len_cls = (uint32_t)r.len | (two_plane ? kTwoPlaneBit : 0u) | ((uint32_t)c64 << 24);
+      m.len_cls = (uint32_t)r.len | layout | ((uint32_t)c64 << 24);
       m.out_off = (uint32_t)(P.reg_out0[k] + (uint64_t)oi * (uint64_t)nh);
       m.hap0 = hap0;
       if (P.finalize) reinterpret_cast<uint32_t*>(base + P.off_rnh)[ridx] = (uint32_t)nh;
@@ -1044,7 +1094,7 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
         for (int32_t j = 0; j < nh; ++j) { e[j].read = (uint32_t)ridx; e[j].hap = hap0 + (uint32_t)j; }
         fill[c64] += (uint32_t)nh;
       }
-      rpos += read_blob_bytes((uint32_t)r.len, two_plane);
+      rpos += read_blob_bytes((uint32_t)r.len, layout);
       ++ridx;
     }
     opos += nr;
@@ -1200,9 +1250,12 @@ int Engine::launch_chunk(Device& d, Slot& s, bool upload, bool download, bool ti
         for (const Task& t : bk.tasks) {
           const ClassDesc& cd = r.tk->classes[t.cls];
           double cols = 0, hl = 0, rl = 0;
-          for (uint32_t j = 0; j < t.n_haps; ++j) { cols += hm[t.hap0 + j].len + cd.G - 1; hl += hm[t.hap0 + j].len; }
+          const bool pr = r.tk->form == 3;  // two haplotype columns per step
+          for (uint32_t j = 0; j < t.n_haps; ++j) hl += hm[t.hap0 + j].len;
+          for (uint32_t j = 0; j < t.n_haps; j += pr ? 2 : 1)
+            cols += std::max(hm[t.hap0 + j].len, (pr && j + 1 < t.n_haps) ? hm[t.hap0 + j + 1].len : 0u) + cd.G - 1;
           for (uint32_t i = 0; i < t.n_reads; ++i) rl += read_len_of(rm[t.read0 + i]);
-          swept += 32.0 * cd.R * cols;
+          swept += (pr ? 64.0 : 32.0) * cd.R * cols;
           useful += rl * hl;
         }
         fprintf(stderr, "[fcs_phmm] f32 launch tier %d form %d key 0x%x tasks %u (%s) smem %zu hs_cap %u stage %u geom_eff %.3f classes%s\n", r.tk->tier,
@@ -2050,7 +2103,10 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
       const ClassDesc& cd = r.tk->classes[t.cls];
       if ((int)t.n_reads > 32 / cd.G || t.n_reads == 0 || t.n_haps == 0) return set_error(FCS_PHMM_EINVAL, "plan_check: task shape");
       double cols = 0, hl = 0, rl = 0;
-      for (uint32_t j = 0; j < t.n_haps; ++j) { cols += hm[t.hap0 + j].len + cd.G - 1; hl += hm[t.hap0 + j].len; }
+      const bool pr = r.tk->form == 3;  // haplotype-pair kernels sweep two columns per step
+      for (uint32_t j = 0; j < t.n_haps; ++j) hl += hm[t.hap0 + j].len;
+      for (uint32_t j = 0; j < t.n_haps; j += pr ? 2 : 1)
+        cols += std::max(hm[t.hap0 + j].len, (pr && j + 1 < t.n_haps) ? hm[t.hap0 + j + 1].len : 0u) + cd.G - 1;
       for (uint32_t i = 0; i < t.n_reads; ++i) {
         const ReadMeta& m = rm[t.read0 + i];
         const uint32_t len = read_len_of(m);
@@ -2061,7 +2117,7 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
           if (oi >= P.n_pairs || seen[oi]++) return set_error(FCS_PHMM_EINVAL, "plan_check: pair covered twice or out of range");
         }
       }
-      swept += 32.0 * cd.R * cols;
+      swept += (pr ? 64.0 : 32.0) * cd.R * cols;
       useful += rl * hl;
     }
   }

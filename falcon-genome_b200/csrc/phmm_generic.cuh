@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(32, 8) phmm_generic(const __grid_constant__ KP
     const ReadMeta rm = p.rmeta[e.read];
     const HapMeta hm = p.hmeta[e.hap];
     const int Lr = (int)read_len_of(rm), Lh = (int)hm.len;
-    const bool two_plane = read_two_plane(rm);
+    const uint32_t layout = read_layout(rm);
     const uint8_t* rs = p.reads + (size_t)rm.data_off16 * 16u;
     const uint8_t* hap = p.haps + (size_t)hm.data_off16 * 16u;
     const int P = (Lr + 1 + C::ROWS - 1) / C::ROWS;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(32, 8) phmm_generic(const __grid_constant__ KP
     T result = T(0);
     for (int s = 0; s < P; ++s) {
       __syncwarp();
-      tile.build(rs, (uint32_t)Lr, lane, lut, mm, tab_lane, true, two_plane, s * C::ROWS, npad);
+      tile.build(rs, (uint32_t)Lr, lane, lut, mm, tab_lane, true, layout, s * C::ROWS, npad);
       if (p.n_sym > (uint32_t)kCodeOther) Tile<T, 32, R, false>::build_other_rows(rs, (uint32_t)Lr, lane, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last, s * C::ROWS, npad);
       __syncwarp();
       State st;

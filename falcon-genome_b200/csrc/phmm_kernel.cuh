@@ -219,11 +219,18 @@ struct Tile {
   // memory for the UA form, which touches only bases and base qualities); len == 0 => no read.
   // row0 / npad: tile row 0 of lane 0 is row `row0` of a striped read whose first `npad` rows are
   // boundary replicas (single pass: row0 = 0, npad = G*R - len).
-  // two_plane: the read is packed as [bases | base quals | trailer {ins, del, gcp}] (constant transition qualities).
+  // layout: the blob's layout flags (phmm_types.h read_layout): which of the insertion / deletion / continuation planes exist; a
+  // missing plane's value comes from the 16-byte trailer {ins, del, gcp} (or, for the deletion plane of a same-indel read, from
+  // the insertion plane).
   __device__ __forceinline__ void build(const uint8_t* rs, uint32_t len, int lig, const T* lut, const T* __restrict__ mm,
-                                        uint8_t* tab_lane, bool with_n, bool two_plane, int row0 = 0, int npad_override = -1) {
+                                        uint8_t* tab_lane, bool with_n, uint32_t layout, int row0 = 0, int npad_override = -1) {
     const uint32_t Lp = round_up16(len);
-    const uint32_t qpl = two_plane ? 1u : Lp;  // distance between the ins / del / gcp values of one read position
+    // byte offset of the insertion / deletion / continuation quality of read position 0 and the stride per position (0 = constant)
+    const uint32_t trailer = read_planes(layout) * Lp;
+    const bool has_i = !(layout & kTwoPlaneBit), has_d = !(layout & (kTwoPlaneBit | kSameIndelBit)), has_c = !(layout & kLayoutMask);
+    const uint32_t off_i = has_i ? 2u * Lp : trailer, off_d = has_d ? 3u * Lp : (has_i ? 2u * Lp : trailer + 1u);
+    const uint32_t off_c = has_c ? 4u * Lp : trailer + 2u;
+    const uint32_t str_i = has_i ? 1u : 0u, str_c = has_c ? 1u : 0u;
     const int npad = (npad_override >= 0 ? npad_override : G * R - (int)len) - row0;
     npl = min(max(npad - lig * R, 0), R);
     off_last = ((threadIdx.x >> 2) & 1) ? -16 : (NV - 1) * 16;
@@ -240,8 +247,7 @@ struct Tile {
         pm = A::sub(T(1), e);
         px = A::div(e, T(3));
         if constexpr (!UA) {
-          const uint32_t qpo = two_plane ? 0u : (uint32_t)pos;
-          const uint32_t iq = rs[2 * Lp + qpo] & 127u, dq = rs[2 * Lp + qpl + qpo] & 127u;
+          const uint32_t iq = rs[off_i + str_i * (uint32_t)pos] & 127u, dq = rs[off_d + str_i * (uint32_t)pos] & 127u;
           const uint32_t mn = min(iq, dq), mx = max(iq, dq);
           pMM[k] = mm[((mx * (mx + 1u)) >> 1) + mn];
           pMX[k] = lut[iq];
@@ -250,7 +256,7 @@ struct Tile {
           pMX[0] = cMX;
         }
         T pc = cXX;
-        if constexpr (!UG) pc = lut[rs[2 * Lp + 2 * qpl + (two_plane ? 0u : (uint32_t)pos)] & 127u];
+        if constexpr (!UG) pc = lut[rs[off_c + str_c * (uint32_t)pos] & 127u];
         gmk = A::sub(T(1), pc);
         xxk = pc;
         yyk = pc;
@@ -395,6 +401,95 @@ struct Tile {
 };
 
 // ----------------------------------------------------------------------------------------
+// Haplotype-pair form (FP32, uniform gap-continuation quality): every lane runs its R read rows against TWO haplotypes
+// of the region at once.  The two cells of a row share the row's transition terms, so the state lives in aligned
+// register pairs and the recurrences run as packed f32x2 instructions (FFMA2 / FMUL2, sm_100a) whose per-row operand
+// is a broadcast scalar register (R.F32) and whose launch constants come from uniform registers: 7 packed + 2 scalar
+// issue slots per TWO cells instead of 16, no register-bank conflicts (a pair reads both banks once).  Each half is
+// an IEEE fp32 operation with round-to-nearest and subnormals, in the statement order of Tile::step => same bits.
+// Measured in isolation (tools/ubench/step_pairs.cu): 9.5-9.8 cycles per warp-cell against 10.4 for the scalar step;
+// the FMA pipe itself (2 cycles per packed instruction) is then the limiter (ncu: 85-87 % busy, math_pipe_throttle).
+// Only the prior multiply stays scalar: the two columns see different haplotype symbols, so their priors come from
+// two table rows.
+template <int G, int R>
+struct PairTile {
+  using T1 = Tile<float, G, R, 1>;
+  static constexpr int NV = T1::NV;
+  static constexpr int UNROLL = 2;
+  static __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+
+  struct State {
+    float2 M[R], X[R], Y[R];
+    float2 dM, dX, dY;
+    float2 acc;
+  };
+
+  static __device__ __forceinline__ float2 shfl_up2(float2 v) {
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1, G), __shfl_up_sync(0xffffffffu, v.y, 1, G));
+  }
+
+  static __device__ __forceinline__ void init(const T1& t, State& st, float2 y_init) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      st.M[k] = bc(0.f);
+      st.X[k] = bc(0.f);
+      st.Y[k] = (k < t.npl) ? y_init : bc(0.f);
+    }
+    st.dM = bc(0.f);
+    st.dX = bc(0.f);
+    st.dY = shfl_up2(st.Y[R - 1]);
+    st.acc = bc(0.f);
+  }
+
+  // one column of each haplotype; prow_a / prow_b = this lane's slice of the prior table for the two symbols
+  static __device__ __forceinline__ void step(const T1& t, State& st, const uint8_t* prow_a, const uint8_t* prow_b, float2 uM, float2 uX, float2 uY) {
+    float pa[NV * 4], pb[NV * 4];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 f = *reinterpret_cast<const float4*>(prow_a + t.chunk_off(v));
+      pa[v * 4 + 0] = f.x; pa[v * 4 + 1] = f.y; pa[v * 4 + 2] = f.z; pa[v * 4 + 3] = f.w;
+      const float4 g = *reinterpret_cast<const float4*>(prow_b + t.chunk_off(v));
+      pb[v * 4 + 0] = g.x; pb[v * 4 + 1] = g.y; pb[v * 4 + 2] = g.z; pb[v * 4 + 3] = g.w;
+    }
+    float2 nM[R], nX[R], nY[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float2 md = k ? st.M[k - 1] : st.dM;
+      const float2 xd = k ? st.X[k - 1] : st.dX;
+      const float2 yd = k ? st.Y[k - 1] : st.dY;
+      float2 s = __fmul2_rn(md, bc(t.pMM[k]));
+      s = __ffma2_rn(xd, bc(t.cGM), s);
+      s = __ffma2_rn(yd, bc(t.cGM), s);
+      nM[k] = make_float2(__fmul_rn(s.x, pa[k]), __fmul_rn(s.y, pb[k]));
+      nY[k] = __ffma2_rn(st.Y[k], bc(t.pYY[k]), __fmul2_rn(st.M[k], bc(t.pMY[k])));
+    }
+    nX[0] = __ffma2_rn(uX, bc(t.pXX[0]), __fmul2_rn(uM, bc(t.pMX[0])));
+#pragma unroll
+    for (int k = 1; k < R; ++k) nX[k] = __ffma2_rn(nX[k - 1], bc(t.cXX), __fmul2_rn(nM[k - 1], bc(t.pMX[k])));
+    st.acc = __fadd2_rn(st.acc, __fadd2_rn(nM[R - 1], nX[R - 1]));
+    st.dM = uM; st.dX = uX; st.dY = uY;
+#pragma unroll
+    for (int k = 0; k < R; ++k) { st.M[k] = nM[k]; st.X[k] = nX[k]; st.Y[k] = nY[k]; }
+  }
+
+  // One haplotype pair.  hs_lane[t] holds the table offsets (16-byte units) of the two columns this lane sees at
+  // step t: low half = first haplotype, high half = second.  Returns the two row sums of this lane's bottom row.
+  static __device__ __forceinline__ float2 run(const T1& t, const uint8_t* tab_lane, const uint32_t* hs_lane, int nsteps, float2 y_init) {
+    State st;
+    init(t, st, y_init);
+#pragma unroll(UNROLL)
+    for (int i = 0; i < nsteps; ++i) {
+      const uint32_t h = hs_lane[i];
+      const float2 uM = shfl_up2(st.M[R - 1]);
+      const float2 uX = shfl_up2(st.X[R - 1]);
+      const float2 uY = shfl_up2(st.Y[R - 1]);
+      step(t, st, tab_lane + (h & 0xffffu) * 16u, tab_lane + (h >> 16) * 16u, uM, uX, uY);
+    }
+    return st.acc;
+  }
+};
+
+// ----------------------------------------------------------------------------------------
 // result emission
 __device__ __forceinline__ void emit_f32(const KParams& p, const ReadMeta& rm, uint32_t read, uint32_t hap, float S) {
   const uint32_t oi = rm.out_off + (hap - rm.hap0);
@@ -451,21 +546,21 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
   const uint32_t read = task.read0 + (active ? grp : 0);
   const ReadMeta rm = p.rmeta[read];
   const uint32_t rlen = active ? read_len_of(rm) : 0u;
-  const bool two_plane = read_two_plane(rm);
+  const uint32_t layout = read_layout(rm);
   const HapMeta h_first = p.hmeta[task.hap0];
   const HapMeta h_last = p.hmeta[task.hap0 + task.n_haps - 1];
   const uint32_t hap_bytes = (h_last.data_off16 - h_first.data_off16) * 16u + round_up16(h_last.len);
   // ---- stage reads + haplotypes with TMA bulk copies
-  const uint32_t my_bytes = ((!UA && active && lig == 0) ? read_blob_bytes(rlen, two_plane) : 0u) + (lane == 0 ? hap_bytes : 0u);
+  const uint32_t my_bytes = ((!UA && active && lig == 0) ? read_blob_bytes(rlen, layout) : 0u) + (lane == 0 ? hap_bytes : 0u);
   const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
   if (lane == 0) mbar_expect_tx(bar, tot);
   __syncwarp();
-  if (!UA && active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, read_blob_bytes(rlen, two_plane), bar);
+  if (!UA && active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, read_blob_bytes(rlen, layout), bar);
   if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
   // ---- per-row constants + prior table (the UA form builds from global memory while the copy flies)
-  if constexpr (UA) tile.build(p.reads + (size_t)rm.data_off16 * 16u, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, two_plane);
+  if constexpr (UA) tile.build(p.reads + (size_t)rm.data_off16 * 16u, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, layout);
   mbar_wait(bar, 0u);
-  if constexpr (!UA) tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, two_plane);
+  if constexpr (!UA) tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, layout);
   if (p.n_sym > (uint32_t)kCodeOther)
     Tile<T, G, R, FORM>::build_other_rows(UA ? p.reads + (size_t)rm.data_off16 * 16u : rstage, rlen, lig, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last);
   __syncwarp();  // every lane is done with the LUT and the read staging before the stream overwrites them
@@ -493,6 +588,88 @@ __device__ __forceinline__ void run_task(const KParams& p, const Task task, uint
     if (active && lig == G - 1) {
       if constexpr (sizeof(T) == 4) emit_f32(p, rm, read, task.hap0 + j, acc);
       else emit_f64(p, rm, task.hap0 + j, acc);
+    }
+  }
+}
+
+// Task form of the haplotype-pair kernels: the task's haplotypes are taken two at a time (an odd run ends with a
+// pair whose second stream is all PAD: its result is dropped).  Stream entries are 32 bits: two table offsets.
+template <int G, int R>
+__device__ __forceinline__ void run_task_pairs(const KParams& p, const Task task, uint8_t* smem) {
+  using L = Layout<float, G, R, false, 1>;
+  using TT = Tile<float, G, R, 1>;
+  using PT = PairTile<G, R>;
+  const int lane = threadIdx.x;
+  const int grp = lane / G, lig = lane % G;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint8_t* tab_lane = smem + L::OFF_TAB + TT::lane_base(lane);
+  uint8_t* un = smem + L::off_union(p.n_sym);
+  float* lut = reinterpret_cast<float*>(un);
+  uint8_t* rstage = un + L::LUT_BYTES + grp * L::RSTAGE;
+  uint32_t* hs = reinterpret_cast<uint32_t*>(un);  // aliases lut + rstage: written only after tile.build
+  uint8_t* hstage = un + L::union_bytes(p.hs_cap);
+  const float* __restrict__ mm = reinterpret_cast<const float*>(p.mm);
+
+  for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const float*>(p.ph2pr)[i];
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  TT tile;
+  tile.cXX = p.c_xx_f; tile.cGM = p.c_gm_f; tile.cMM = p.c_mm_f; tile.cMX = p.c_mx_f;
+
+  const bool active = grp < (int)task.n_reads;
+  const uint32_t read = task.read0 + (active ? grp : 0);
+  const ReadMeta rm = p.rmeta[read];
+  const uint32_t rlen = active ? read_len_of(rm) : 0u;
+  const uint32_t layout = read_layout(rm);
+  const HapMeta h_first = p.hmeta[task.hap0];
+  const HapMeta h_last = p.hmeta[task.hap0 + task.n_haps - 1];
+  const uint32_t hap_bytes = (h_last.data_off16 - h_first.data_off16) * 16u + round_up16(h_last.len);
+  const uint32_t my_bytes = ((active && lig == 0) ? read_blob_bytes(rlen, layout) : 0u) + (lane == 0 ? hap_bytes : 0u);
+  const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
+  if (lane == 0) mbar_expect_tx(bar, tot);
+  __syncwarp();
+  if (active && lig == 0) bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, read_blob_bytes(rlen, layout), bar);
+  if (lane == 0) bulk_g2s(hstage, p.haps + (size_t)h_first.data_off16 * 16u, hap_bytes, bar);
+  mbar_wait(bar, 0u);
+  tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, layout);
+  if (p.n_sym > (uint32_t)kCodeOther) TT::build_other_rows(rstage, rlen, lig, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last);
+  __syncwarp();
+  // ---- pair stream: [G-1 PAD] pair0 [G-1 PAD] pair1 ... [G-1 PAD]; a pair is max(len_a, len_b) entries long
+  constexpr uint32_t kPad = (uint32_t)(kCodePad * L::HSCALE);
+  constexpr uint32_t kPad2 = kPad | (kPad << 16);
+  const uint32_t n_pairs = (task.n_haps + 1u) / 2u;
+  uint32_t off = 0;
+  for (uint32_t q = 0; q < n_pairs; ++q) {
+    const HapMeta ha = p.hmeta[task.hap0 + 2u * q];
+    const bool has_b = 2u * q + 1u < task.n_haps;
+    const HapMeta hb = has_b ? p.hmeta[task.hap0 + 2u * q + 1u] : ha;
+    const uint32_t len_b = has_b ? hb.len : 0u;
+    const uint32_t lmax = max(ha.len, len_b);
+    const uint8_t* sa = hstage + (ha.data_off16 - h_first.data_off16) * 16u;
+    const uint8_t* sb = hstage + (hb.data_off16 - h_first.data_off16) * 16u;
+    if (lane < G - 1) hs[off + lane] = kPad2;
+    for (uint32_t x = lane; x < lmax; x += 32) {
+      const uint32_t ca = x < ha.len ? (uint32_t)(hap_code(sa[x], p.n_sym, p.extra_bytes) * L::HSCALE) : kPad;
+      const uint32_t cb = x < len_b ? (uint32_t)(hap_code(sb[x], p.n_sym, p.extra_bytes) * L::HSCALE) : kPad;
+      hs[off + (G - 1) + x] = ca | (cb << 16);
+    }
+    off += (G - 1) + lmax;
+  }
+  if (lane < G - 1) hs[off + lane] = kPad2;
+  __syncwarp();
+  // ---- wavefront over every haplotype pair of the task
+  off = 0;
+  for (uint32_t q = 0; q < n_pairs; ++q) {
+    const uint32_t la = p.hmeta[task.hap0 + 2u * q].len;
+    const bool has_b = 2u * q + 1u < task.n_haps;
+    const uint32_t lb = has_b ? p.hmeta[task.hap0 + 2u * q + 1u].len : 0u;
+    const uint32_t lmax = max(la, lb);
+    const float2 y_init = make_float2(__fdiv_rn(0x1p120f, (float)(int)la), has_b ? __fdiv_rn(0x1p120f, (float)(int)lb) : 0.f);
+    const float2 acc = PT::run(tile, tab_lane, hs + off + (G - 1) - lig, (int)lmax + G - 1, y_init);
+    off += (G - 1) + lmax;
+    if (active && lig == G - 1) {
+      emit_f32(p, rm, read, task.hap0 + 2u * q, acc.x);
+      if (has_b) emit_f32(p, rm, read, task.hap0 + 2u * q + 1u, acc.y);
     }
   }
 }
@@ -535,22 +712,22 @@ __device__ __forceinline__ void run_queue(const KParams& p, uint32_t qid, uint32
     const ReadMeta rm = p.rmeta[e.read];
     const HapMeta hm = p.hmeta[e.hap];
     const uint32_t rlen = active ? read_len_of(rm) : 0u;
-    const bool two_plane = read_two_plane(rm);
+    const uint32_t layout = read_layout(rm);
     const uint32_t Lh = active ? hm.len : 0u;
     // the LUT shares its shared memory with the haplotype stream of the previous round: reload it
     for (int i = lane; i < 128; i += 32) lut[i] = reinterpret_cast<const T*>(p.ph2pr)[i];
     fence_proxy_async();  // staging / stream were touched through the generic proxy last round
-    const uint32_t my_bytes = (active && lig == 0) ? read_blob_bytes(rlen, two_plane) + round_up16(Lh) : 0u;
+    const uint32_t my_bytes = (active && lig == 0) ? read_blob_bytes(rlen, layout) + round_up16(Lh) : 0u;
     const uint32_t tot = __reduce_add_sync(0xffffffffu, my_bytes);
     if (lane == 0) mbar_expect_tx(bar, tot);
     __syncwarp();
     if (active && lig == 0) {
-      bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, read_blob_bytes(rlen, two_plane), bar);
+      bulk_g2s(rstage, p.reads + (size_t)rm.data_off16 * 16u, read_blob_bytes(rlen, layout), bar);
       bulk_g2s(hstage, p.haps + (size_t)hm.data_off16 * 16u, round_up16(Lh), bar);
     }
     mbar_wait(bar, parity);
     parity ^= 1u;
-    tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, two_plane);
+    tile.build(rstage, rlen, lig, lut, mm, tab_lane, p.n_sym > 5u, layout);
     if (p.n_sym > (uint32_t)kCodeOther) Tile<T, G, R, FORM>::build_other_rows(rstage, rlen, lig, lut, tab_lane, p.n_sym, p.extra_bytes, tile.off_last);
     __syncwarp();  // done with the LUT and the read staging before the stream overwrites them
     const uint32_t Lmax = __reduce_max_sync(0xffffffffu, Lh);

@@ -8,6 +8,7 @@
 namespace fcsphmm {
 
 #define PHMM_CASE_TASK(I, G, R) case I: run_task<T, G, R, FORM>(p, task, smem); break;
+#define PHMM_CASE_PAIR(I, G, R) case I: run_task_pairs<G, R>(p, task, smem); break;
 #define PHMM_CASE_QUEUE(I, G, R) case I: run_queue<T, G, R, FORM>(p, qid, cta, nctas, smem); break;
 
 #define PHMM_DEFINE_TASK_KERNEL(NAME, T_, FORM_, MINB_, LIST_MACRO)                                   \
@@ -17,6 +18,14 @@ namespace fcsphmm {
     extern __shared__ __align__(128) uint8_t smem[];                                               \
     const Task task = p.tasks[blockIdx.x];                                                         \
     switch (task.cls) { LIST_MACRO(PHMM_CASE_TASK) default: break; }                               \
+  }
+
+// haplotype-pair form (FP32, uniform gap-continuation quality): T_ / FORM_ are fixed, kept for a uniform macro signature
+#define PHMM_DEFINE_PAIR_KERNEL(NAME, T_, FORM_, MINB_, LIST_MACRO)                                   \
+  __global__ void __launch_bounds__(32, MINB_) NAME(const __grid_constant__ KParams p) {          \
+    extern __shared__ __align__(128) uint8_t smem[];                                               \
+    const Task task = p.tasks[blockIdx.x];                                                         \
+    switch (task.cls) { LIST_MACRO(PHMM_CASE_PAIR) default: break; }                               \
   }
 
 #define PHMM_DEFINE_QUEUE_KERNEL(NAME, T_, FORM_, MINB_, LIST_MACRO)                                  \

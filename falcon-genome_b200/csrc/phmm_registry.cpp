@@ -10,14 +10,14 @@
 
 namespace fcsphmm {
 
-extern const TierKernel kTierF32T0, kTierF32T1, kTierF32T2, kTierF32UT0, kTierF32UT1, kTierF32UT2, kTierF32AT1, kTierF32AT2;
+extern const TierKernel kTierF32T0, kTierF32T1, kTierF32T2, kTierF32UT0, kTierF32UT1, kTierF32UT2, kTierF32AT1, kTierF32AT2, kTierF32PT1, kTierF32PT2;
 extern const TierKernel kTierF64T0, kTierF64T1, kTierF64T2, kTierF64UT0, kTierF64UT1, kTierF64UT2;
 
 namespace {
-const TierKernel* g_kernels[] = {&kTierF32T0, &kTierF32T1, &kTierF32T2, &kTierF32UT0, &kTierF32UT1, &kTierF32UT2, &kTierF32AT1, &kTierF32AT2,
+const TierKernel* g_kernels[] = {&kTierF32T0, &kTierF32T1, &kTierF32T2, &kTierF32UT0, &kTierF32UT1, &kTierF32UT2, &kTierF32AT1, &kTierF32AT2, &kTierF32PT1, &kTierF32PT2,
                                  &kTierF64T0, &kTierF64T1, &kTierF64T2, &kTierF64UT0, &kTierF64UT1, &kTierF64UT2};
-constexpr int kNumKernels = 14;
-constexpr int kForms = 3;  // general, uniform-GCP, all-uniform
+constexpr int kNumKernels = 16;
+constexpr int kForms = 4;  // general, uniform-GCP, all-uniform, haplotype pairs (uniform GCP)
 inline int fidx(bool f64, int form) { return (f64 ? kForms : 0) + form; }
 constexpr int kMaxSelLen = 1024;
 std::vector<ClassRef> g_classes[2 * kForms];    // [fidx(f64, form)]
@@ -77,7 +77,7 @@ void build() {
   }
   for (const ClassRef& k : g_classes[fidx(true, 0)]) g_f64_queues.emplace_back(k.G, k.R);
   for (int f = 0; f < 2 * kForms; ++f) {
-    if (f % kForms == 2) continue;  // the all-uniform form has its own class list, no twin
+    if (f % kForms >= 2) continue;  // the all-uniform and the haplotype-pair form have their own class lists, no twin
     for (ClassRef& k : g_classes[f])
       for (const ClassRef& o : g_classes[f - f % kForms + (1 - f % kForms)])
         if (o.G == k.G && o.R == k.R) { k.twin = &o; break; }

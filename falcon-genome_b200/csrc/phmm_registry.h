@@ -18,6 +18,7 @@ struct TierKernel {
   bool f64;        // double-precision, queue-driven rerun kernel
   int form;        // 0 general; 1 uniform gap-continuation quality (pGM / pXX from the constant bank);
                    // 2 all-uniform (pMM / pMX / pMY as well; FP32 only)
+                   // 3 haplotype pairs: uniform gap-continuation quality, two haplotypes per lane in packed f32x2 arithmetic (FP32 only)
   int tier;        // 0: 16 CTAs/SM (<=128 regs), 1: 12 (<=168), 2: 8 (<=255)
   int min_blocks;  // __launch_bounds__ residency target (one-warp CTAs per SM)
   int n_classes;
@@ -34,7 +35,7 @@ struct ClassRef {
   size_t smem_bytes(uint32_t hs_cap, uint32_t hap_stage, uint32_t n_sym) const { return tk->classes[cls].smem_bytes(hs_cap, hap_stage, n_sym); }
 };
 
-// All compiled kernels (14).
+// All compiled kernels (16).
 const TierKernel* const* tier_kernels(int* n);
 // Cheapest class covering a read of this length (rows needed = len + 1) when every lane group of the
 // warp is filled, or nullptr.

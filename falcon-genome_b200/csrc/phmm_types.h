@@ -40,7 +40,7 @@ constexpr int kQueueGenericF64 = kMaxF64Classes - 1;  // FP64 rerun queue of the
 
 struct ReadMeta {
   uint32_t data_off16;  // offset of the read blob in `reads`, in 16-byte units
-  uint32_t len_cls;     // len | two-plane flag << 23 | (fp64 class id << 24)
+  uint32_t len_cls;     // len | layout flags (bits 21-23, see read_layout) | (fp64 class id << 24)
   uint32_t out_off;     // index in out[] of (this read, first hap of its region)
   uint32_t hap0;        // first hap (chunk-wide index) of its region
 };
@@ -107,11 +107,26 @@ struct KParams {
 };
 
 PHMM_HD inline constexpr uint32_t round_up16(uint32_t x) { return (x + 15u) & ~15u; }
+// Read blob layouts (flag bits of ReadMeta::len_cls; the packer decides per read, every kernel form reads all of them):
+//   none of the bits : five planes [bases | base_q | ins_q | del_q | gcp]
+//   kNoGcpPlaneBit   : the gap-continuation quality is one constant (what GATK always passes): no gcp plane,
+//                      a 16-byte trailer {ins, del, gcp} follows the planes (only its gcp byte is used)
+//   kSameIndelBit    : (with kNoGcpPlaneBit) the deletion qualities equal the insertion qualities position by position
+//                      (GATK writes them from one PCR-model value): no del plane either -> [bases | base_q | ins_q | trailer]
+//   kTwoPlaneBit     : insertion, deletion and continuation quality are each one constant -> [bases | base_q | trailer]
 constexpr uint32_t kTwoPlaneBit = 1u << 23;
-PHMM_HD inline uint32_t read_len_of(const ReadMeta& m) { return m.len_cls & 0x7fffffu; }
+constexpr uint32_t kNoGcpPlaneBit = 1u << 22;
+constexpr uint32_t kSameIndelBit = 1u << 21;
+constexpr uint32_t kLayoutMask = kTwoPlaneBit | kNoGcpPlaneBit | kSameIndelBit;
+PHMM_HD inline uint32_t read_len_of(const ReadMeta& m) { return m.len_cls & 0x1fffffu; }
+PHMM_HD inline uint32_t read_layout(const ReadMeta& m) { return m.len_cls & kLayoutMask; }
 PHMM_HD inline bool read_two_plane(const ReadMeta& m) { return (m.len_cls & kTwoPlaneBit) != 0u; }
-PHMM_HD inline constexpr uint32_t read_blob_bytes(uint32_t len, bool two_plane) {
-  return two_plane ? 2u * round_up16(len) + 16u : 5u * round_up16(len);
+// planes a layout stores (bases and base qualities always)
+PHMM_HD inline constexpr uint32_t read_planes(uint32_t layout) {
+  return (layout & kTwoPlaneBit) ? 2u : ((layout & kNoGcpPlaneBit) ? ((layout & kSameIndelBit) ? 3u : 4u) : 5u);
+}
+PHMM_HD inline constexpr uint32_t read_blob_bytes(uint32_t len, uint32_t layout) {
+  return read_planes(layout) * round_up16(len) + ((layout & kLayoutMask) ? 16u : 0u);
 }
 
 // Table lane stride in bytes: smallest odd multiple of 16 that holds R values of size esz.

@@ -10,7 +10,9 @@ namespace fcsphmm {
 #define TT float
 #endif
 #define LIST1(X) X(0, GG, RR)
-#if defined(QUEUE_KERNEL)
+#if defined(PAIR_KERNEL)
+PHMM_DEFINE_PAIR_KERNEL(one_class_kernel, float, 3, MINB, LIST1)
+#elif defined(QUEUE_KERNEL)
 PHMM_DEFINE_QUEUE_KERNEL(one_class_kernel, TT, FORM_, MINB, LIST1)
 #else
 PHMM_DEFINE_TASK_KERNEL(one_class_kernel, TT, FORM_, MINB, LIST1)

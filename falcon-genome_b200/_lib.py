@@ -56,7 +56,7 @@ class PlanInfo(C.Structure):
     _fields_ = [("n_pairs", C.c_int64), ("n_tasks", C.c_int64), ("n_generic_pairs", C.c_int64), ("in_bytes", C.c_int64),
                 ("max_smem_bytes", C.c_int64), ("n_launches_f32", C.c_int32), ("n_launches_f64", C.c_int32), ("n_sym", C.c_int32),
                 ("latency_mode", C.c_int32), ("geometric_efficiency", C.c_double), ("plan_ms", C.c_double), ("pack_ms", C.c_double),
-                ("n_tasks_general", C.c_int64), ("n_tasks_uniform_gcp", C.c_int64), ("n_tasks_all_uniform", C.c_int64)]
+                ("n_tasks_general", C.c_int64), ("n_tasks_uniform_gcp", C.c_int64), ("n_tasks_all_uniform", C.c_int64), ("n_tasks_hap_pairs", C.c_int64)]
 
 
 class Stats(C.Structure):

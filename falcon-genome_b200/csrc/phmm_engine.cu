@@ -593,6 +593,7 @@ struct Planner {
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps, ukeys;
     std::vector<uint32_t> layouts;
+    std::vector<uint8_t> paired;  // per read of the region (sorted order): its even haplotypes ran on the haplotype-pair kernels
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
     int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
     size_t reads_bytes = 0, haps_bytes = 0;
@@ -682,6 +683,7 @@ struct Planner {
       for (int32_t j = 0; j < nh; ++j) maxlh = std::max(maxlh, hlens[j]);
       const bool long_hap = maxlh >= (uint32_t)kGenericMinHapLen;
       s.gen_flags.resize(read_base + (size_t)nr, 0);
+      paired.assign((size_t)nr, 0);
       for (int32_t i = 0; i < nr;) {
         const double pairs_left = (double)(pairs_after[k + 1] + (uint64_t)(nr - i) * (uint64_t)nh);
         const bool tail1 = shape_tail && pairs_left <= tail1_x * (double)wave_pairs;
@@ -775,15 +777,8 @@ struct Planner {
           }
         };
         if (kp) {
-          const int tg = gcps[ord[i]];
-          const int32_t n_even = nh & ~1;
-          emit(kp, tg, 0, cnt, 0, n_even, true);
-          if (nh & 1) {
-            // the odd haplotype: scalar uniform-GCP class of the longest read, as many tasks as its lane groups need
-            const ClassRef* ks = (k0->twin && k0->tk->form == 0) ? k0->twin : k0;
-            const int ngs = 32 / ks->G;
-            for (int32_t r0 = 0; r0 < cnt; r0 += ngs) emit(ks, ks->tk->form ? tg : -1, r0, std::min<int32_t>(ngs, cnt - r0), nh - 1, nh, false);
-          }
+          emit(kp, gcps[ord[i]], 0, cnt, 0, nh & ~1, true);
+          for (int32_t x = 0; x < cnt; ++x) paired[(size_t)(i + x)] = 1;  // an odd last haplotype is handled below
         } else {
           int tg = gcps[ord[i]];  // uniform-GCP form only if every read of the task shares the value
           for (int32_t x = 1; x < cnt; ++x)
@@ -793,6 +788,47 @@ struct Planner {
           emit(kc, tg, 0, cnt, 0, nh, false);
         }
         i += cnt;
+      }
+      if (nh & 1) {
+        // The odd last haplotype of the reads that ran on the pair kernels: scalar uniform-GCP classes, grouped on
+        // their own (a scalar class may seat more reads per warp than the pair class did).
+        for (int32_t a = 0; a < nr;) {
+          if (!paired[(size_t)a]) { ++a; continue; }
+          int32_t b = a;
+          while (b < nr && paired[(size_t)b]) ++b;
+          for (int32_t i = a; i < b;) {
+            const int len0 = (int)lens[ord[i]];
+            const bool fine0 = len0 > 1024 || (fine_len[(size_t)len0] & 1u);
+            const ClassRef* k0 = fine0 ? f32_class_of_len(0, len0) : f32_coarse_class_of_len(0, len0);
+            if (b - i < 32 / k0->G) k0 = select_class_for(false, false, len0, b - i, (int)hlens[nh - 1], !fine0);
+            const int cnt = std::min<int32_t>(32 / k0->G, b - i);
+            int tg = gcps[ord[i]];
+            for (int32_t x = 1; x < cnt; ++x)
+              if (gcps[ord[i + x]] != tg) tg = -1;
+            const ClassRef* kc = (tg >= 0 && k0->twin) ? k0->twin : k0;
+            TaskBucket* bk = nullptr;
+            for (auto& bb : s.buckets)
+              if (bb.tk == kc->tk && bb.gcp == tg) { bk = &bb; break; }
+            if (!bk) {
+              s.buckets.emplace_back();
+              bk = &s.buckets.back();
+              bk->tk = kc->tk;
+              bk->gcp = tg;
+            }
+            Task t;
+            t.read0 = read_base + (uint32_t)i;
+            t.hap0 = hap_base + (uint32_t)(nh - 1);
+            t.n_reads = (uint16_t)cnt;
+            t.n_haps = 1;
+            t.cls = (uint32_t)kc->cls;
+            bk->tasks.push_back(t);
+            bk->hs = std::max(bk->hs, hlens[nh - 1] + 2u * (uint32_t)(kc->G - 1));
+            bk->stage = std::max(bk->stage, round_up16(hlens[nh - 1]));
+            bk->cls_mask |= 1ull << kc->cls;
+            i += cnt;
+          }
+          a = b;
+        }
       }
       const double tp3 = g_plan_prof ? now_ms() : 0;
       // ---- FP64 queue capacity per class (worst case: every pair of the read falls back)
@@ -2080,10 +2116,10 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
   out->n_tasks = (int64_t)P.n_tasks;
   out->n_generic_pairs = (int64_t)P.n_gen;
   out->n_launches_f32 = 0;
-  out->n_tasks_general = out->n_tasks_uniform_gcp = out->n_tasks_all_uniform = 0;
+  out->n_tasks_general = out->n_tasks_uniform_gcp = out->n_tasks_all_uniform = out->n_tasks_hap_pairs = 0;
   for (const auto& r : P.f32) {
     out->n_launches_f32 += r.n_tasks ? 1 : 0;
-    (r.tk->form == 2 ? out->n_tasks_all_uniform : (r.tk->form == 1 ? out->n_tasks_uniform_gcp : out->n_tasks_general)) += (int64_t)r.n_tasks;
+    (r.tk->form == 3 ? out->n_tasks_hap_pairs : (r.tk->form == 2 ? out->n_tasks_all_uniform : (r.tk->form == 1 ? out->n_tasks_uniform_gcp : out->n_tasks_general))) += (int64_t)r.n_tasks;
   }
   out->n_launches_f32 += P.n_gen ? 1 : 0;
   out->n_launches_f64 = (int32_t)P.f64.size() + (P.gen64_cap ? 1 : 0);

@@ -279,6 +279,8 @@ typedef struct {
   double plan_ms, pack_ms;
   /* FP32 tasks per kernel form: general, uniform gap-continuation quality, all transition qualities uniform */
   int64_t n_tasks_general, n_tasks_uniform_gcp, n_tasks_all_uniform;
+  /* FP32 tasks of the haplotype-pair kernels (uniform gap-continuation quality, two haplotypes per lane in packed f32x2 arithmetic) */
+  int64_t n_tasks_hap_pairs;
 } fcs_phmm_plan_info;
 FCS_PHMM_API int fcs_pairhmm_plan_check(const fcs_phmm_flat_batch* b, int32_t sm_count, fcs_phmm_plan_info* out);
 /* The transition / prior lookup tables the kernels use, for bit-level checks against the oracle

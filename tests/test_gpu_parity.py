@@ -197,6 +197,56 @@ def test_all_uniform_form_underflow_fallback(hmm, oracle):
     check_against_oracle(oracle, b, out, used, raw, simd=False)
 
 
+def _pcr_model_region(rng, L, n_reads, hap, gcp=10, same_indel=True):
+    """Reads as GATK's PCR indel model leaves them: insertion == deletion quality per position (lower inside
+    homopolymer runs), one gap-continuation quality; same_indel=False breaks the equality on some positions."""
+    reads = []
+    for _ in range(n_reads):
+        s = int(rng.integers(0, max(1, len(hap) - L)))
+        bases = bytearray((hap + hap + hap + hap)[s:s + L])
+        for x in range(L):
+            if rng.random() < 0.02:
+                bases[x] = int(rng.choice(list(b"ACGTN")))
+        q = bytes(rng.integers(6, 42, L).astype(np.uint8))
+        i = np.full(L, 45, np.uint8)
+        i[rng.random(L) < 0.1] = rng.integers(10, 40)
+        d = i.copy()
+        if not same_indel:
+            d[rng.random(L) < 0.05] = 33
+        reads.append((bytes(bases), q, bytes(i), bytes(d), bytes([gcp]) * L))
+    return reads
+
+
+def test_haplotype_pair_kernels(hmm, oracle):
+    """Reads with one gap-continuation quality run against their haplotypes two at a time (packed f32x2 kernels):
+    sweep the pair classes (exact tile fits included), odd and even haplotype counts, pairs of very different lengths,
+    N in haplotypes, reads whose deletion qualities differ from the insertion qualities (four-plane blobs) and groups
+    whose reads disagree on the continuation quality (scalar fallback).  Bit-identical raw sums are the bar."""
+    from falcon_genome_b200 import plan_check
+
+    rng = np.random.default_rng(31337)
+    hap = bytes(rng.choice(list(b"ACGT"), 420).astype(np.uint8))
+    hap_n = bytearray(hap[30:330]); hap_n[11] = ord("N"); hap_n[250] = ord("N")
+    pool = [hap, hap[:100], hap[50:], bytes(hap_n), hap[200:], hap[5:395], hap[100:160]]
+    lens = [40, 64, 95, 96, 103, 104, 127, 128, 150, 151, 152, 159, 160, 175, 191, 192, 200, 239, 250, 255, 256, 300, 319, 320, 383]
+    regs = []
+    for n, L in enumerate(lens):
+        nh = [2, 3, 4, 5, 7][n % 5]
+        reads = _pcr_model_region(rng, L, [8, 5, 9, 3][n % 4], hap, same_indel=(n % 3 != 0))
+        regs.append(Region(reads, [pool[(n + j) % len(pool)] for j in range(nh)]))
+    mixed = _pcr_model_region(rng, 150, 6, hap, gcp=10) + _pcr_model_region(rng, 150, 6, hap, gcp=12)
+    regs.append(Region(mixed, [hap, hap[7:300], hap[60:]]))
+    # filler: keeps the regions above out of the tail-shaping window (the last ~1.5 waves of a call use other classes)
+    for _ in range(220):
+        regs.append(Region(_pcr_model_region(rng, 150, 8, hap), [hap[:300], hap[20:310], hap[40:345], hap[3:290]]))
+    b = FlatBatch.from_regions(regs)
+    assert plan_check(b)["n_tasks_hap_pairs"] > 0
+    out, used, raw = hmm.compute_flat(b, want_raw=True)
+    check_against_oracle(oracle, b, out, used, raw, simd=False)
+    out2, used2 = hmm.compute_regions(b)  # the chunked path (tail shaping only on the last chunk)
+    assert np.array_equal(out, out2) and np.array_equal(used, used2)
+
+
 def test_golden_fixtures(hmm):
     """Committed fixtures (tools/make_golden.py, oracle-scored): bit-exact raw FP32 sums and fallback
     flags, FP64 reruns to 1e-9, everything within the 1e-4 contract of the double-precision value."""

@@ -154,8 +154,9 @@ def test_planner_picks_the_kernel_form_from_the_qualities():
 
     def forms(regs):
         i = plan_check(FlatBatch.from_regions(regs))
-        assert i["n_tasks"] == i["n_tasks_general"] + i["n_tasks_uniform_gcp"] + i["n_tasks_all_uniform"]
-        return i["n_tasks_general"], i["n_tasks_uniform_gcp"], i["n_tasks_all_uniform"]
+        assert i["n_tasks"] == i["n_tasks_general"] + i["n_tasks_uniform_gcp"] + i["n_tasks_all_uniform"] + i["n_tasks_hap_pairs"]
+        # (the haplotype-pair kernels are the throughput variant of the uniform-GCP form: counted with it)
+        return i["n_tasks_general"], i["n_tasks_uniform_gcp"] + i["n_tasks_hap_pairs"], i["n_tasks_all_uniform"]
 
     big = 400  # regions: well above the tail-shaping window, which uses wide uniform-GCP classes
     g, u, a = forms([region(32, 150, 45, 45, 10) for _ in range(big)])
@@ -169,6 +170,48 @@ def test_planner_picks_the_kernel_form_from_the_qualities():
     minority = [region(16, 150, 45, 45, 10) for _ in range(big // 4)] + [region(16, 150, 45, 40, 10) for _ in range(big)]
     g, u, a = forms(minority)
     assert a == 0 and u > 0
+
+
+def test_compact_read_layouts_and_haplotype_pairs():
+    """Host-only: the packer drops planes that carry no information (constant gap-continuation quality -> trailer;
+    deletion plane == insertion plane -> not copied; all three constant -> two planes), and reads with one
+    continuation quality take the haplotype-pair kernels for an even number of haplotypes, the scalar form for the odd one."""
+    from falcon_genome_b200 import plan_check
+
+    rng = np.random.default_rng(11)
+    hap = bytes(rng.choice(list(b"ACGT"), 300).astype(np.uint8))
+    L, n_reg, n_reads = 160, 300, 16  # L = 160: planes need no padding
+
+    def batch(kind, haps):
+        regs = []
+        for _ in range(n_reg):
+            reads = []
+            for r in range(n_reads):
+                i = bytearray([45] * L)
+                d = bytearray([45] * L)
+                c = bytearray([10] * L)
+                if kind >= 1:
+                    i[r + 3] = 30; d[r + 3] = 30  # per-position, insertion == deletion
+                if kind >= 2:
+                    d[r + 9] = 31                 # deletion plane differs
+                if kind >= 3:
+                    c[r + 1] = 11                 # continuation quality not constant
+                reads.append((hap[:L], bytes([30] * L), bytes(i), bytes(d), bytes(c)))
+            regs.append(Region(reads, haps))
+        return plan_check(FlatBatch.from_regions(regs))
+
+    one = [batch(k, [hap]) for k in range(4)]  # one haplotype per region: no pair kernels, same task count in every form
+    n = n_reg * n_reads
+    assert one[1]["n_tasks"] == one[2]["n_tasks"] == one[3]["n_tasks"]
+    assert one[2]["in_bytes"] - one[1]["in_bytes"] == n * L          # + deletion plane
+    assert one[3]["in_bytes"] - one[2]["in_bytes"] == n * (L - 16)   # + continuation plane - trailer
+    assert one[1]["in_bytes"] > one[0]["in_bytes"]                   # + insertion plane (the all-uniform form cuts other tasks)
+    assert all(o["n_tasks_hap_pairs"] == 0 for o in one)
+    five = batch(1, [hap, hap[10:290], hap[5:280], hap[20:300], hap[1:299]])
+    assert five["n_tasks_hap_pairs"] > 0 and five["n_tasks_uniform_gcp"] > 0 and five["n_tasks_general"] == 0
+    four = batch(2, [hap, hap[10:290], hap[5:280], hap[20:300]])
+    assert four["n_tasks_hap_pairs"] > 0
+    assert batch(3, [hap, hap[10:290]])["n_tasks_hap_pairs"] == 0  # per-read continuation quality not constant
 
 
 # ---- property test of the batcher (hypothesis): any ragged call shape is covered exactly once ----------
@@ -220,6 +263,6 @@ def test_property_batcher_covers_any_call_shape(shape, seed):
     info = plan_check(b)
     assert info["n_pairs"] == b.n_pairs
     assert info["n_tasks"] + info["n_generic_pairs"] > 0
-    assert info["n_tasks"] == info["n_tasks_general"] + info["n_tasks_uniform_gcp"] + info["n_tasks_all_uniform"]
+    assert info["n_tasks"] == info["n_tasks_general"] + info["n_tasks_uniform_gcp"] + info["n_tasks_all_uniform"] + info["n_tasks_hap_pairs"]
     assert info["max_smem_bytes"] <= 227 * 1024
     assert 0.0 < info["geometric_efficiency"] <= 1.0

@@ -79,32 +79,45 @@ static inline const ClassRef* f32_class_of_len(int form, int len) { return (len 
 static inline const ClassRef* f32_coarse_class_of_len(int form, int len) { return (len >= 1 && len <= 1024) ? g_f32_coarse_by_len[form][len] : nullptr; }
 static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid_by_len[len] : -1; }
 
-// The value all qualities of one plane of a read share (masked & 127 like the kernels), or -1.
-// Runs over every read of every call (up to three planes): 16 bytes per step, early exit.
-static int uniform_gcp(const uint8_t* c, int32_t len) {
-  const uint8_t v = c[0] & 127u;
-  // fast path: all bytes equal <=> c[0..len-1) == c[1..len); libc's memcmp is dispatched to the widest vectors of the
-  // host and stops at the first difference.  Bytes with the top bit set (masked by the kernels) take the loop below.
-  if (len > 1 && std::memcmp(c, c + 1, (size_t)len - 1) == 0) return (int)v;
-  if (len == 1) return (int)v;
-  int32_t i = 0;
+// One pass over the three transition-quality planes of a read (runs once per read of every call):
+//   gcp / ins / del = the value all bytes of the plane share (masked & 127 like the kernels), or -1;
+//   same_indel      = the deletion plane equals the insertion plane byte for byte.
+struct QualScan { int gcp, ins, del; bool same_indel; };
+static inline QualScan scan_quals(const uint8_t* c, const uint8_t* i, const uint8_t* d, int32_t len) {
+  QualScan r;
 #if defined(__SSE2__)
-  const __m128i vv = _mm_set1_epi8((char)v), m7 = _mm_set1_epi8(0x7f);
-  for (; i + 16 <= len; i += 16) {
-    const __m128i w = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i*>(c + i)), m7);
-    if (_mm_movemask_epi8(_mm_cmpeq_epi8(w, vv)) != 0xffff) return -1;
-  }
-#else
-  const uint64_t v8 = 0x0101010101010101ull * v, mask7 = 0x7f7f7f7f7f7f7f7full;
-  for (; i + 8 <= len; i += 8) {
-    uint64_t w;
-    std::memcpy(&w, c + i, 8);
-    if ((w & mask7) != v8) return -1;
+  if (len >= 16) {
+    const __m128i c0 = _mm_set1_epi8((char)c[0]), i0 = _mm_set1_epi8((char)i[0]), d0 = _mm_set1_epi8((char)d[0]);
+    __m128i ac = _mm_setzero_si128(), ai = ac, ad = ac, aid = ac;
+    auto block = [&](int32_t x) {
+      const __m128i vc = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c + x));
+      const __m128i vi = _mm_loadu_si128(reinterpret_cast<const __m128i*>(i + x));
+      const __m128i vd = _mm_loadu_si128(reinterpret_cast<const __m128i*>(d + x));
+      ac = _mm_or_si128(ac, _mm_xor_si128(vc, c0));
+      ai = _mm_or_si128(ai, _mm_xor_si128(vi, i0));
+      ad = _mm_or_si128(ad, _mm_xor_si128(vd, d0));
+      aid = _mm_or_si128(aid, _mm_xor_si128(vi, vd));
+    };
+    int32_t x = 0;
+    for (; x + 16 <= len; x += 16) block(x);
+    if (x < len) block(len - 16);  // the last, partly filled block overlaps the previous one
+    const __m128i m7 = _mm_set1_epi8(0x7f), z = _mm_setzero_si128();
+    r.gcp = _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_and_si128(ac, m7), z)) == 0xffff ? (int)(c[0] & 127u) : -1;
+    r.ins = _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_and_si128(ai, m7), z)) == 0xffff ? (int)(i[0] & 127u) : -1;
+    r.del = _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_and_si128(ad, m7), z)) == 0xffff ? (int)(d[0] & 127u) : -1;
+    r.same_indel = _mm_movemask_epi8(_mm_cmpeq_epi8(aid, z)) == 0xffff;
+    return r;
   }
 #endif
-  for (; i < len; ++i)
-    if ((c[i] & 127u) != v) return -1;
-  return (int)v;
+  uint8_t ac = 0, ai = 0, ad = 0, aid = 0;
+  for (int32_t x = 0; x < len; ++x) {
+    ac |= (uint8_t)(c[x] ^ c[0]); ai |= (uint8_t)(i[x] ^ i[0]); ad |= (uint8_t)(d[x] ^ d[0]); aid |= (uint8_t)(i[x] ^ d[x]);
+  }
+  r.gcp = (ac & 127u) ? -1 : (int)(c[0] & 127u);
+  r.ins = (ai & 127u) ? -1 : (int)(i[0] & 127u);
+  r.del = (ad & 127u) ? -1 : (int)(d[0] & 127u);
+  r.same_indel = aid == 0;
+  return r;
 }
 
 // dst[0, round_up16(len)) = src[0, len) followed by `pad` bytes.  The packer runs this ten times per read on
@@ -533,24 +546,18 @@ struct Planner {
         for (int32_t i = 0; i < nr; ++i) {
           const InRead r = in.read(regions[kk], i);
           int gq = -1, uk = -1;
+          uint32_t lay = 0;
           if (r.len > 0 && r.i && r.d && r.c) {
-            gq = uniform_gcp(r.c, r.len);
-            if (gq >= 0) {
-              const int ui = uniform_gcp(r.i, r.len);
-              const int ud = ui >= 0 ? uniform_gcp(r.d, r.len) : -1;
-              // (equal insertion and deletion quality, as GATK writes them: the kernels share M * pMX = M * pMY)
-              if (ud >= 0 && ud == ui) uk = gq | (ui << 8) | (ud << 16);
-            }
+            const QualScan qs = scan_quals(r.c, r.i, r.d, r.len);
+            gq = qs.gcp;
+            // (equal insertion and deletion quality, as GATK writes them: the kernels share M * pMX = M * pMY)
+            if (gq >= 0 && qs.ins >= 0 && qs.del == qs.ins) uk = gq | (qs.ins << 8) | (qs.del << 16);
+            // compact blob layouts: constant qualities travel in a 16-byte trailer, a deletion plane equal to the insertion
+            // plane (GATK writes both from one value) is not copied at all
+            if (two_plane_enabled() && gq >= 0) lay = uk >= 0 ? kTwoPlaneBit : (kNoGcpPlaneBit | (qs.same_indel ? kSameIndelBit : 0u));
           }
           all_gcp.push_back(gq);
           all_ukey.push_back(uk);
-          // compact blob layouts: constant qualities travel in a 16-byte trailer, a deletion plane equal to the insertion
-          // plane (GATK writes both from one value) is not copied at all
-          uint32_t lay = 0;
-          if (two_plane_enabled() && gq >= 0) {
-            if (uk >= 0) lay = kTwoPlaneBit;
-            else lay = kNoGcpPlaneBit | (std::memcmp(r.i, r.d, (size_t)r.len) == 0 ? kSameIndelBit : 0u);
-          }
           all_layout.push_back(lay);
           n_elig += uk >= 0;
           if (r.len >= 1 && r.len <= 1024) ++len_hist[(size_t)r.len];

@@ -309,7 +309,8 @@ int Engine::init(const fcs_phmm_config* cfg) {
       const TierKernel* const* tks = tier_kernels(&nk);
       for (int i = 0; i < nk; ++i) CK(tks[i]->set_max_smem(prop.sharedMemPerBlockOptin));
     }
-    d->slots.resize(nslots);
+    d->slots = std::vector<Slot>((size_t)nslots);
+    d->use.assign((size_t)pack_threads_, 0);
     static const bool numa_bind = env_i64("FCS_PHMM_NUMA_BIND", 0) != 0;  // opt-in, see Device::node_cpus
     cpu_set_t before;
     bool rebound = false;
@@ -373,7 +374,17 @@ static void free_slot(Slot& s) {
   if (s.ev_k2) cudaEventDestroy(s.ev_k2);
   if (s.ev_done) cudaEventDestroy(s.ev_done);
   if (s.stream) cudaStreamDestroy(s.stream);
-  s = Slot();
+  // back to the state of a fresh slot (not `s = Slot()`: the slot's mutex is neither copyable nor movable)
+  s.stream = nullptr;
+  s.ev_k0 = s.ev_k1 = s.ev_k2 = s.ev_done = s.ev_fork = nullptr;
+  for (int i = 0; i < Slot::kSide; ++i) { s.side[i] = nullptr; s.ev_side[i] = nullptr; }
+  for (int i = 0; i < Slot::kHp; ++i) { s.hp[i] = nullptr; s.ev_hp[i] = nullptr; }
+  s.h_in = s.h_out = s.d_buf = nullptr;
+  s.h_in_cap = s.h_out_cap = s.d_cap = 0;
+  s.busy = s.timed = false;
+  s.owner = nullptr;
+  s.input = nullptr;
+  s.plan = ChunkPlan();
 }
 
 Engine::~Engine() {
@@ -1395,10 +1406,25 @@ static cudaEvent_t g_tl_ref = nullptr;
 static std::mutex g_tl_mu;
 static std::string g_tl_gpu;
 
-int Engine::retire_slot(Device& d, Slot& s) {
+int Engine::retire_slot(Device& d, Slot& s, BatchCtx* only_owner) {
   (void)d;
-  if (!s.busy) return FCS_PHMM_OK;
+  std::lock_guard<std::mutex> slot_lock(s.mu);
+  if (!s.busy || (only_owner && s.owner != only_owner)) return FCS_PHMM_OK;
+  const int rc = retire_locked(s);
+  // the chunk is gone whatever happened: tell its batch (which may not be the caller's: a worker of the next batch
+  // retires what it finds in the slot it is about to reuse)
+  BatchCtx* o = s.owner;
   s.busy = false;
+  s.owner = nullptr;
+  if (o) {
+    std::lock_guard<std::mutex> l(o->mu);
+    if (rc != FCS_PHMM_OK && o->rc == FCS_PHMM_OK) { o->rc = rc; o->err = last_error(); }
+    if (o->pending.fetch_sub(1) == 1) o->cv.notify_all();
+  }
+  return rc;
+}
+
+int Engine::retire_locked(Slot& s) {
   const double tw0 = now_ms();
   CK(cudaEventSynchronize(s.ev_done));
   const double tw1 = now_ms();
@@ -1588,11 +1614,11 @@ static int validate_input(const Input& in) {
   return FCS_PHMM_OK;
 }
 
-// compute_one() behind a firewall: nothing thrown on the host side of a batch (std::bad_alloc from the planner's
+// compute_front() behind a firewall: nothing thrown on the host side of a batch (std::bad_alloc from the planner's
 // vectors is the realistic case) may leave the flat-combining leader section.
-int Engine::compute_one_noexcept(const Input& in) {
+int Engine::compute_front_noexcept(const Input& in, BatchCtx& ctx) {
   try {
-    return compute_one(in);
+    return compute_front(in, ctx);
   } catch (const std::bad_alloc&) {
     return set_error(FCS_PHMM_ENOMEM, "host allocation failed");
   } catch (const std::exception& ex) {
@@ -1618,6 +1644,7 @@ int Engine::compute(const Input& in) {
   me.in = &in;
   std::unique_lock<std::mutex> lk(comb_mu_);
   comb_queue_.push_back(&me);
+  comb_waiting_.fetch_add(1);
   while (!me.done) {
     if (comb_leader_) {
       comb_cv_.wait(lk);
@@ -1626,32 +1653,63 @@ int Engine::compute(const Input& in) {
     comb_leader_ = true;
     std::vector<PendingCall*> batch;
     batch.swap(comb_queue_);  // (no allocation: swap)
+    comb_waiting_.fetch_sub((int)batch.size());
     lk.unlock();
     // Leader section.  Whatever happens here, every call of the batch is marked done with a result and the
     // leadership is given up: a caller left waiting would hang its JVM thread for good.
+    // The leader role covers the FRONT phase only (plan + pack + launch of every chunk).  It is handed on before the
+    // batch's last chunks have left the devices, so the next batch's sizing, planning and packing overlap this one's tail
+    // (a call on eight devices spends as long in its serial prefix and its first chunk as on the devices).
+    bool front_released = false;
+    auto release_front = [&] {
+      if (front_released) return;
+      front_released = true;
+      std::lock_guard<std::mutex> l(comb_mu_);
+      comb_leader_ = false;
+      comb_cv_.notify_all();
+    };
     try {
+      BatchCtx ctx;
+      int rc;
       if (batch.size() == 1) {
-        batch[0]->rc = compute_one_noexcept(*batch[0]->in);
-        if (batch[0]->rc != FCS_PHMM_OK) batch[0]->err = last_error();
+        rc = compute_front_noexcept(*batch[0]->in, ctx);
+        std::string err = rc != FCS_PHMM_OK ? last_error() : std::string();
+        release_front();
+        const int rc2 = compute_back(ctx);
+        if (rc == FCS_PHMM_OK && rc2 != FCS_PHMM_OK) { rc = rc2; err = last_error(); }
+        batch[0]->rc = rc;
+        if (rc != FCS_PHMM_OK) batch[0]->err = err;
       } else {
         std::vector<const Input*> parts;
         for (PendingCall* c : batch) parts.push_back(c->in);
         CombinedInput all(parts);
-        int rc = compute_one_noexcept(all);
+        rc = compute_front_noexcept(all, ctx);
+        release_front();
+        const int rc2 = compute_back(ctx);  // (`all` stays alive until every chunk that points at it has been retired)
+        if (rc == FCS_PHMM_OK) rc = rc2;
         if (rc != FCS_PHMM_OK) {
+          // a call of the merged batch is malformed (or a device failed): re-run call by call, so that only its owner
+          // sees the error; serial, each call front + back under the leader role
+          {
+            std::unique_lock<std::mutex> l(comb_mu_);
+            comb_cv_.wait(l, [&] { return !comb_leader_; });
+            comb_leader_ = true;
+            front_released = false;
+          }
           for (PendingCall* c : batch) {
-            c->rc = compute_one_noexcept(*c->in);
+            c->rc = compute_whole(*c->in);
             if (c->rc != FCS_PHMM_OK) c->err = last_error();
           }
+          release_front();
         }
       }
     } catch (...) {  // allocation of `parts` / CombinedInput / an error string
       for (PendingCall* c : batch)
         if (c->rc == FCS_PHMM_OK) c->rc = FCS_PHMM_ENOMEM;  // err text stays empty: assigning it could throw again
     }
+    release_front();
     lk.lock();
     for (PendingCall* c : batch) c->done = true;
-    comb_leader_ = false;
     comb_cv_.notify_all();
   }
   lk.unlock();
@@ -1659,11 +1717,42 @@ int Engine::compute(const Input& in) {
   return FCS_PHMM_OK;
 }
 
-int Engine::compute_one(const Input& in) {
+int Engine::compute_whole(const Input& in) {
+  BatchCtx ctx;
+  int rc = compute_front_noexcept(in, ctx);
+  const std::string err = rc != FCS_PHMM_OK ? last_error() : std::string();
+  const int rc2 = compute_back(ctx);
+  if (rc != FCS_PHMM_OK) return set_error(rc, err);
+  return rc2;
+}
+
+// Back phase of a batch: retire whatever is still in flight for it, wait for the chunks other threads are retiring.
+int Engine::compute_back(BatchCtx& ctx) {
+  int rc = FCS_PHMM_OK;
+  std::string err;
+  for (auto& dp : devs_) {
+    if (ctx.pending.load() == 0) break;
+    bool set = false;
+    for (Slot& s : dp->slots) {
+      if (ctx.pending.load() == 0) break;
+      if (!set) { cudaSetDevice(dp->ordinal); set = true; }
+      const int r = retire_slot(*dp, s, &ctx);
+      if (r != FCS_PHMM_OK && rc == FCS_PHMM_OK) { rc = r; err = last_error(); }
+    }
+  }
+  std::unique_lock<std::mutex> l(ctx.mu);
+  ctx.cv.wait(l, [&] { return ctx.pending.load() == 0; });
+  if (rc == FCS_PHMM_OK && ctx.rc != FCS_PHMM_OK) { rc = ctx.rc; err = ctx.err; }
+  l.unlock();
+  if (rc != FCS_PHMM_OK) return set_error(rc, err);
+  return FCS_PHMM_OK;
+}
+
+int Engine::compute_front(const Input& in, BatchCtx& ctx) {
   const int64_t n = in.n_regions();
   if (n < 0) return set_error(FCS_PHMM_EINVAL, "negative region count");
   if (n == 0) return FCS_PHMM_OK;
-  std::lock_guard<std::mutex> call_lock(compute_mu_);
+  std::lock_guard<std::mutex> call_lock(front_mu_);
   const size_t D = devs_.size();
   const uint32_t hs_cols = (uint32_t)env_i64("FCS_PHMM_HS_COLS", 640);
   static const bool timeline = env_i64("FCS_PHMM_TIMELINE", 0) != 0;  // developer knob: host timeline of the call on stderr
@@ -1819,8 +1908,12 @@ int Engine::compute_one(const Input& in) {
       }
       if (cudaSetDevice(devs_[d]->ordinal) != cudaSuccess) return set_error(FCS_PHMM_ECUDA, "cudaSetDevice failed");
       for (int sidx = 0; sidx < 2 * work[d].threads; ++sidx) {
-        const int rc = ensure_buffers(devs_[d]->slots[(size_t)sidx], need_in, need_out, need_tot);
-        if (rc != FCS_PHMM_OK) return rc;
+        Slot& sl = devs_[d]->slots[(size_t)sidx];
+        if (need_in > sl.h_in_cap || need_out > sl.h_out_cap || need_tot > sl.d_cap) {
+          int rc = retire_slot(*devs_[d], sl);  // the previous batch's chunk may still be using the buffers
+          if (rc == FCS_PHMM_OK) rc = ensure_buffers(sl, need_in, need_out, need_tot);
+          if (rc != FCS_PHMM_OK) return rc;
+        }
       }
     }
     for (int w = 0; w < work[d].threads; ++w) jobs.emplace_back((int)d, w);
@@ -1844,7 +1937,7 @@ int Engine::compute_one(const Input& in) {
     const int w = jobs[(size_t)job].second;
     if (cudaSetDevice(d.ordinal) != cudaSuccess) { set_error(FCS_PHMM_ECUDA, "cudaSetDevice failed"); fail_with(FCS_PHMM_ECUDA); return; }
     if (d.has_node_cpus && t_pool_thread) sched_setaffinity(0, sizeof(cpu_set_t), &d.node_cpus);  // never the caller's own thread
-    int use = 0;
+    int& use = d.use[(size_t)w];  // (one worker per (device, w) at a time: the front phase is exclusive)
     while (first_rc.load() == FCS_PHMM_OK) {
       const size_t c = dw.next.fetch_add(1);
       if (c >= dw.chunks.size()) break;
@@ -1876,14 +1969,23 @@ int Engine::compute_one(const Input& in) {
       tl_mark("packed", w, c);
       rc = launch_chunk(d, s, true, true, chunk_timing);
       if (rc != FCS_PHMM_OK) { cudaStreamSynchronize(s.stream); fail_with(rc); break; }
-      s.busy = true;
+      {
+        std::lock_guard<std::mutex> sl(s.mu);
+        ctx.pending.fetch_add(1);
+        s.owner = &ctx;
+        s.busy = true;
+      }
       tl_mark("launched", w, c);
     }
-    for (int k = 0; k < 2; ++k) {
-      int r2 = retire_slot(d, d.slots[(size_t)2 * w + k]);
-      if (r2 != FCS_PHMM_OK) fail_with(r2);
-      tl_mark("drained", w, (size_t)k);
-    }
+    // Nobody queued behind this batch: drain this worker's own slots here, in parallel with the other workers (the
+    // scatter of a large call is ~0.1 ms per chunk).  Otherwise leave the chunks in flight to the next batch's workers,
+    // whose front phase starts as soon as this one ends, and to the back phase.
+    if (comb_waiting_.load() == 0)
+      for (int k = 0; k < 2; ++k) {
+        int r2 = retire_slot(d, d.slots[(size_t)2 * w + k], &ctx);
+        if (r2 != FCS_PHMM_OK) fail_with(r2);
+        tl_mark("drained", w, (size_t)k);
+      }
    } catch (...) {  // pool threads have no caller to unwind to (std::bad_alloc from the planner's vectors is the realistic case)
     set_error(FCS_PHMM_ENOMEM, "host allocation failed in a packing thread");
     fail_with(FCS_PHMM_ENOMEM);
@@ -1891,8 +1993,14 @@ int Engine::compute_one(const Input& in) {
     Device& d = *devs_[(size_t)jobs[(size_t)job].first];
     for (int k = 0; k < 2; ++k) {
       Slot& s = d.slots[(size_t)2 * jobs[(size_t)job].second + k];
-      if (s.busy) cudaEventSynchronize(s.ev_done);
-      s.busy = false;
+      std::lock_guard<std::mutex> sl(s.mu);
+      if (s.busy && s.owner == &ctx) {
+        cudaEventSynchronize(s.ev_done);
+        s.busy = false;
+        s.owner = nullptr;
+        std::lock_guard<std::mutex> l(ctx.mu);
+        if (ctx.pending.fetch_sub(1) == 1) ctx.cv.notify_all();
+      }
     }
    }
   };

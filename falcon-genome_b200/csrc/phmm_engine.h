@@ -111,7 +111,20 @@ struct ChunkPlan {
   int launches() const;
 };
 
+// One batch of compute() between its front phase (plan + pack + launch, exclusive) and the moment its last chunk has been
+// retired (results scattered).  Chunks are retired by whoever needs their slot next -- a worker of the same batch, a worker
+// of the NEXT batch (whose front phase overlaps this batch's tail on the devices) or the batch's own leader in its back phase.
+struct BatchCtx {
+  std::atomic<int> pending{0};  // chunks launched and not yet retired
+  std::mutex mu;
+  std::condition_variable cv;
+  int rc = 0;                   // first error met while retiring a chunk of this batch (guarded by mu)
+  std::string err;
+};
+
 struct Slot {
+  std::mutex mu;                // guards busy / owner / the retirement of the chunk in flight
+  BatchCtx* owner = nullptr;    // batch of the chunk in flight (busy)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_k2 = nullptr, ev_done = nullptr;
   // kernels of different classes are forked onto side streams so that their tails overlap
@@ -152,6 +165,7 @@ struct Device {
   void* d_ph2pr_d = nullptr;
   void* d_mm_d = nullptr;
   std::vector<Slot> slots;
+  std::vector<int> use;  // per packing thread: which of its two slots comes next (kept across batches: the older chunk retires first)
   std::mutex mu;  // one call at a time drives a device's slots
   // FCS_PHMM_NUMA_BIND=1 (opt-in): the cores of the NUMA node the GPU hangs off, intersected with the process's
   // affinity mask.  Pool threads that work for this device run there and its pinned staging is allocated from there.
@@ -201,8 +215,10 @@ class Engine {
   static int create(const fcs_phmm_config* cfg, Engine** out);
   ~Engine();
   int compute(const Input& in);       // coalesces concurrent callers into one device batch
-  int compute_one(const Input& in);   // one batch, caller holds the device (compute_mu_)
-  int compute_one_noexcept(const Input& in);
+  int compute_front(const Input& in, BatchCtx& ctx);  // one batch: plan, pack and launch every chunk (exclusive: front_mu_)
+  int compute_back(BatchCtx& ctx);                    // wait until every chunk of the batch has been retired
+  int compute_front_noexcept(const Input& in, BatchCtx& ctx);
+  int compute_whole(const Input& in);                 // front + back
   int submit(std::unique_ptr<Input> in, std::shared_ptr<void> keepalive, fcs_phmm_ticket* t);
   int wait(fcs_phmm_ticket t);
   int batch_create(const fcs_phmm_flat_batch* b, int device_index, Batch** out);
@@ -222,7 +238,8 @@ class Engine {
   int init(const fcs_phmm_config* cfg);
   int pack_chunk(Slot& s, const Input& in);
   int launch_chunk(Device& d, Slot& s, bool upload, bool download, bool timing);
-  int retire_slot(Device& d, Slot& s);
+  int retire_slot(Device& d, Slot& s, BatchCtx* only_owner = nullptr);
+  int retire_locked(Slot& s);  // wait for the chunk, scatter its results (caller holds s.mu)
   int ensure_buffers(Slot& s, size_t in_bytes, size_t out_bytes, size_t dev_bytes);
   void fill_kparams(const Device& d, const Slot& s, KParams& p, bool f64) const;
 
@@ -244,7 +261,7 @@ class Engine {
   fcs_phmm_ticket next_ticket_ = 1;
   std::unique_ptr<CaptureWriter> capture_;
   std::unique_ptr<WorkerPool> pool_;
-  std::mutex compute_mu_;  // one batch at a time drives the slots and the pool
+  std::mutex front_mu_;  // one batch at a time plans, packs and launches (its chunks may still be on the devices when the next one starts)
   // flat combining of concurrent compute() calls: the caller that finds no leader becomes one and runs
   // everything queued so far as ONE batch; the others sleep until their call is marked done
   struct PendingCall {
@@ -257,6 +274,7 @@ class Engine {
   std::condition_variable comb_cv_;
   std::vector<PendingCall*> comb_queue_;
   bool comb_leader_ = false;
+  std::atomic<int> comb_waiting_{0};  // calls queued and not yet taken by a leader
   friend struct Batch;
 };
 

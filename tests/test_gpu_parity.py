@@ -546,6 +546,51 @@ def test_concurrent_callers_on_one_handle(hmm):
     assert not errs, errs[:3]
 
 
+def test_pipelined_batches_and_a_failing_caller(hmm):
+    """Concurrent multi-chunk calls: a batch's front phase (plan + pack + launch) overlaps the previous batch's tail on the
+    device, chunks are retired by whoever needs their slot next.  Results must equal the single-threaded ones; a caller
+    whose input the batcher refuses gets its error every time, alone (the merged batch is re-run call by call), and nobody hangs."""
+    import threading
+
+    from falcon_genome_b200 import PairHMMError
+
+    batches = [synth.config3_wgs(n_regions=150, seed=900 + i) for i in range(4)] + [synth.config1_golden(n_regions=40, seed=77)]
+    ref = [hmm.compute_flat(b) for b in batches]
+    many = bytes(range(ord("a"), ord("a") + 12))  # > 8 foreign byte values shared by read and haplotype: FCS_PHMM_EUNSUPPORTED
+    bad = FlatBatch.from_regions([Region([(many, bytes([30] * 12), bytes([45] * 12), bytes([45] * 12), bytes([10] * 12))], [many])])
+    errs, refused = [], [0]
+
+    def good(tid):
+        try:
+            for rep in range(5):
+                for k in range(len(batches)):
+                    kk = (k + tid) % len(batches)
+                    out, used = hmm.compute_regions(batches[kk]) if (rep + tid) % 2 else hmm.compute_flat(batches[kk])
+                    if not (np.array_equal(out, ref[kk][0]) and np.array_equal(used, ref[kk][1])):
+                        errs.append((tid, rep, kk))
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    def faulty():
+        for _ in range(25):
+            try:
+                hmm.compute_flat(bad)
+                errs.append("the refused call went through")
+            except PairHMMError as e:
+                if e.code != -5:
+                    errs.append(("code", e.code))
+                refused[0] += 1
+
+    th = [threading.Thread(target=good, args=(t,)) for t in range(5)] + [threading.Thread(target=faulty)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=240)
+    assert not any(t.is_alive() for t in th), "a caller hangs"
+    assert not errs, errs[:3]
+    assert refused[0] == 25
+
+
 @pytest.mark.parametrize("seed", [101, 102, 103])
 def test_fuzz_random_shapes_and_bytes(hmm, oracle, seed):
     """Randomised regions: any read length 1..420, haplotype length 1..700, quals over the whole byte

@@ -17,7 +17,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "falcon-genome_b200", "csrc")
 INS = re.compile(r"^\s+/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)\s*(.*?);")
-MATH = ("FFMA", "FMUL", "DFMA", "DMUL")
+MATH = ("FFMA", "FMUL", "DFMA", "DMUL", "FFMA2", "FMUL2")  # (packed f32x2 forms: the haplotype-pair kernels)
 
 
 def functions(sass):
@@ -81,7 +81,7 @@ def audit_objects(out):
             for t, a, body, n_math in loops:
                 shfl = sum(1 for _, op, _, _ in body if op.startswith("SHFL"))
                 sp = sum(1 for _, op, _, _ in body if op.startswith("STL") or op.startswith("LDL"))
-                steps = max(1, round(shfl / (6 if "f64" in name or "double" in name else 3)))
+                steps = max(1, round(shfl / (6 if "f64" in name or "double" in name or "f32p" in name else 3)))
                 (main if steps >= 2 or "generic" in name else rem).append((sp, len(body)))
             m = re.search(re.escape(name) + r".*?(\d+) bytes spill stores, (\d+) bytes spill loads.*?Used (\d+) registers", log, re.S)
             sp_txt = f"{m.group(1)} / {m.group(2)} B" if m else "?"
@@ -135,10 +135,12 @@ def loop_listing(out, tag, title, defs):
 def main():
     out = ["# SASS audit of the PairHMM kernels (tools/sass_audit.py; `cuobjdump -sass` of the objects of this build)\n"]
     audit_objects(out)
-    out.append("## 2. Wavefront loop bodies of the two classes DESIGN.md quotes\n")
+    out.append("## 2. Wavefront loop bodies of the classes DESIGN.md quotes\n")
     loop_listing(out, "ua_g4r38", "All-uniform form, G=4, R=38 (config 2: 150-bp reads on four lanes), 2 steps per trip = 76 cells per lane", ["-DGG=4", "-DRR=38", "-DFORM_=2", "-DMINB=8"])
     loop_listing(out, "ug_g8r19", "Uniform-GCP form, G=8, R=19 (150-bp reads with per-position indel qualities: config 4, PCR-model HaplotypeCaller), 4 steps per trip = 76 cells per lane",
                  ["-DGG=8", "-DRR=19", "-DFORM_=1", "-DMINB=12"])
+    loop_listing(out, "pair_g8r19", "Haplotype-pair form (uniform GCP, two haplotype columns per lane in packed f32x2 arithmetic), G=8, R=19, 4 steps per trip = 152 cells per lane",
+                 ["-DGG=8", "-DRR=19", "-DPAIR_KERNEL", "-DMINB=8"])
     loop_listing(out, "f64u_g16r10", "FP64 rerun, uniform-GCP form, G=16, R=10 (250-bp reads of config 5), queue kernel", ["-DGG=16", "-DRR=10", "-DFORM_=1", "-DMINB=12", "-DTT=double", "-DQUEUE_KERNEL"])
     open(os.path.join(ROOT, "profiles", "r02_sass_audit.md"), "w").write("\n".join(out) + "\n")
     print("\n".join(out))

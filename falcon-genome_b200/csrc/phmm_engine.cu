@@ -611,6 +611,7 @@ struct Planner {
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
     std::vector<int> gcps, ukeys;
     std::vector<uint32_t> layouts;
+    size_t last_bucket = 0;  // the bucket the previous task went to (nearly always the next one's too)
     std::vector<uint8_t> paired;  // per read of the region (sorted order): its even haplotypes ran on the haplotype-pair kernels
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
     int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
@@ -679,16 +680,20 @@ struct Planner {
       const size_t ord0 = s.order.size();
       s.order.resize(ord0 + nr);
       uint32_t* ord = s.order.data() + ord0;
-      std::iota(ord, ord + nr, 0u);
-      bool same = true;
-      for (int32_t i = 1; i < nr && same; ++i) same = lens[i] == lens[0];
-      if (!same) {
-        // descending length, ties in the caller's order: one packed key per read, plain sort (std::stable_sort allocates a
-        // scratch buffer per call, and this runs once per region)
-        sort_keys.resize((size_t)nr);
-        for (int32_t i = 0; i < nr; ++i) sort_keys[(size_t)i] = ((uint64_t)(0xffffffffu - lens[i]) << 32) | (uint32_t)i;
+      // Descending length, ties in the caller's order.  Nearly every read of a region has the region's (maximum) length:
+      // those keep their order up front, only the few shorter (clipped) ones are sorted -- one packed key per read, plain
+      // sort (std::stable_sort allocates a scratch buffer per call, and this runs once per region).
+      uint32_t maxlen = 0;
+      for (int32_t i = 0; i < nr; ++i) maxlen = std::max(maxlen, lens[i]);
+      sort_keys.clear();
+      int32_t n_top = 0;
+      for (int32_t i = 0; i < nr; ++i) {
+        if (lens[i] == maxlen) ord[n_top++] = (uint32_t)i;
+        else sort_keys.push_back(((uint64_t)(0xffffffffu - lens[i]) << 32) | (uint32_t)i);
+      }
+      if (!sort_keys.empty()) {
         std::sort(sort_keys.begin(), sort_keys.end());
-        for (int32_t i = 0; i < nr; ++i) ord[i] = (uint32_t)(sort_keys[(size_t)i] & 0xffffffffu);
+        for (size_t x = 0; x < sort_keys.size(); ++x) ord[n_top + (int32_t)x] = (uint32_t)(sort_keys[x] & 0xffffffffu);
       }
       const double tp2 = g_plan_prof ? now_ms() : 0;
       // ---- tasks
@@ -761,13 +766,15 @@ struct Planner {
         // tasks of reads [i + r0, i + r0 + rc) x haplotypes [j0, j1) for class kc (pairs: two haplotypes per wavefront step)
         auto emit = [&](const ClassRef* kc, int tg, int32_t r0, int32_t rc, int32_t j0, int32_t j1, bool pairs) {
           TaskBucket* bk = nullptr;
-          for (auto& b : s.buckets)
-            if (b.tk == kc->tk && b.gcp == tg) { bk = &b; break; }
+          if (last_bucket < s.buckets.size() && s.buckets[last_bucket].tk == kc->tk && s.buckets[last_bucket].gcp == tg) bk = &s.buckets[last_bucket];
+          for (size_t bi = 0; !bk && bi < s.buckets.size(); ++bi)
+            if (s.buckets[bi].tk == kc->tk && s.buckets[bi].gcp == tg) { bk = &s.buckets[bi]; last_bucket = bi; }
           if (!bk) {
             s.buckets.emplace_back();
             bk = &s.buckets.back();
             bk->tk = kc->tk;
             bk->gcp = tg;
+            last_bucket = s.buckets.size() - 1;
           }
           const int32_t hstep = pairs ? 2 : 1;
           for (int32_t j = j0; j < j1;) {

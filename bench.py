@@ -348,7 +348,7 @@ def measure_config(hmm, hmm_raw, batch, name, n_sm, f_max, steps, want_parity=Tr
 
 def dispatcher_leg(n_dev, args, f_max, n_sm):
     """ONE library handle over all n_dev devices (Engine::compute: regions partitioned by cells, no exchange) fed a
-    fixed config-3 stream (20 calls of 2000 regions) and config 4 (200 regions in 10 calls) through
+    fixed config-3 stream (20 calls of 2000 regions) and config 4 (30 calls of 20 regions over 10 distinct batches) through
     fcs_pairhmm_compute with host buffers; wall clock.  The same stream at every N: strong scaling."""
     from falcon_genome_b200 import PairHMM, RegionArray
 
@@ -361,20 +361,19 @@ def dispatcher_leg(n_dev, args, f_max, n_sm):
     res = {"devices": n_dev, "generation_s": gen_s, "host_threads": host_threads()}
     with PairHMM(devices=list(range(n_dev))) as hm:
         res["device_count"] = hm.device_count
-        for key, batches, calls in (("c3_stream", c3, 20), ("c4", c4, 10)):
+        for key, batches, calls in (("c3_stream", c3, 20), ("c4", c4, 30)):
             callers = args.dispatcher_callers
             if calls > len(batches):  # a batch's result arrays are written by one call at a time
                 callers = min(callers, len(batches))
             ras = [RegionArray(b) for b in batches]
-            for k in range(min(2, len(batches))):
-                hm.compute_regions(batches[k], ras[k])  # warm-up: slot buffers grow to the chunk sizes
-            hm.reset_stats()
             cells = sum(batches[k % len(batches)].cells for k in range(calls))
             # the calls are issued by `callers` threads, as GATK's native PairHMM threads (HTCWorker.cpp:85) or the JVMs
-            # of a stage do; the library coalesces calls that arrive while a batch is on the devices (flat combining)
+            # of a stage do; the library coalesces calls that arrive while a batch is on the devices (flat combining) and
+            # overlaps a batch's planning with the previous batch's tail (cross-batch pipelining)
             nxt = [0]
             lock = threading.Lock()
             errs = []
+            n_calls = [calls]
 
             def caller():
                 try:
@@ -382,11 +381,25 @@ def dispatcher_leg(n_dev, args, f_max, n_sm):
                         with lock:
                             k = nxt[0]
                             nxt[0] += 1
-                        if k >= calls:
+                        if k >= n_calls[0]:
                             return
                         hm.compute_regions(batches[k % len(batches)], ras[k % len(batches)])
                 except Exception as e:  # noqa: BLE001
                     errs.append(repr(e))
+
+            # warm-up with the same concurrency as the timed pass: merged batches cut larger chunks than single calls, and the
+            # slot buffers must have grown to them before the clock starts (re-allocating pinned memory costs milliseconds)
+            n_calls[0] = min(calls, 2 * callers)
+            ths = [threading.Thread(target=caller) for _ in range(callers)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            if errs:
+                raise RuntimeError("dispatcher leg (warm-up): " + errs[0])
+            nxt[0] = 0
+            n_calls[0] = calls
+            hm.reset_stats()
 
             ths = [threading.Thread(target=caller) for _ in range(callers)]
             t0 = time.perf_counter()
@@ -416,7 +429,8 @@ def dispatcher_leg(n_dev, args, f_max, n_sm):
             res[key]["ok"] = bool(same and p["ok"])
     res["ok"] = bool(res["c3_stream"]["ok"] and res["c4"]["ok"])
     res["note"] = ("strong scaling: the same stream at every N; one process, one handle, pack_threads = min(4, cores / N) per device, calls issued by "
-                   "`callers` threads; value = cells / wall seconds from the first call to the last return (generation and RegionArray construction excluded)")
+                   "`callers` threads after a warm-up pass with the same concurrency; value = cells / wall seconds from the first call to the last return (generation and "
+                   "RegionArray construction excluded)")
     return res
 
 

@@ -1635,6 +1635,21 @@ int Engine::compute_front_noexcept(const Input& in, BatchCtx& ctx) {
   }
 }
 
+// Drains a batch on scope exit unless finish() already did: a BatchCtx must outlive every chunk whose slot points at it.
+struct Engine::BackGuard {
+  Engine* e;
+  BatchCtx* ctx;
+  bool done = false;
+  int finish() { done = true; return e->compute_back(*ctx); }
+  ~BackGuard() {
+    if (done) return;
+    try { e->compute_back(*ctx); } catch (...) {}
+    // (compute_back throws only while formatting an error; the chunks are retired before that.  Should even the wait be
+    // cut short, block until the count is zero: returning earlier would leave dangling owners.)
+    while (ctx->pending.load() != 0) std::this_thread::yield();
+  }
+};
+
 int Engine::compute(const Input& in) {
   // Per call, before it can join a batch: the capture hook -- once per original call (a failing merged batch is
   // re-run call by call below and must not be captured twice), and only for calls that pass the structural checks,
@@ -1653,7 +1668,10 @@ int Engine::compute(const Input& in) {
   comb_queue_.push_back(&me);
   comb_waiting_.fetch_add(1);
   while (!me.done) {
-    if (comb_leader_) {
+    // sleep while another leader is in its front phase -- or while there is nothing to lead: this caller's own call may
+    // already be part of a batch whose leader has handed the role on and is waiting for the devices (the queue is then
+    // empty until new calls arrive, and their callers take the role themselves)
+    if (comb_leader_ || comb_queue_.empty()) {
       comb_cv_.wait(lk);
       continue;
     }
@@ -1676,13 +1694,14 @@ int Engine::compute(const Input& in) {
       comb_cv_.notify_all();
     };
     try {
-      BatchCtx ctx;
       int rc;
       if (batch.size() == 1) {
+        BatchCtx ctx;
+        BackGuard guard{this, &ctx};  // whatever is thrown below, ctx is not destroyed while a chunk in flight points at it
         rc = compute_front_noexcept(*batch[0]->in, ctx);
         std::string err = rc != FCS_PHMM_OK ? last_error() : std::string();
         release_front();
-        const int rc2 = compute_back(ctx);
+        const int rc2 = guard.finish();
         if (rc == FCS_PHMM_OK && rc2 != FCS_PHMM_OK) { rc = rc2; err = last_error(); }
         batch[0]->rc = rc;
         if (rc != FCS_PHMM_OK) batch[0]->err = err;
@@ -1690,9 +1709,11 @@ int Engine::compute(const Input& in) {
         std::vector<const Input*> parts;
         for (PendingCall* c : batch) parts.push_back(c->in);
         CombinedInput all(parts);
+        BatchCtx ctx;
+        BackGuard guard{this, &ctx};  // (declared after `all`: the merged input outlives every chunk that points at it)
         rc = compute_front_noexcept(all, ctx);
         release_front();
-        const int rc2 = compute_back(ctx);  // (`all` stays alive until every chunk that points at it has been retired)
+        const int rc2 = guard.finish();
         if (rc == FCS_PHMM_OK) rc = rc2;
         if (rc != FCS_PHMM_OK) {
           // a call of the merged batch is malformed (or a device failed): re-run call by call, so that only its owner
@@ -1726,9 +1747,10 @@ int Engine::compute(const Input& in) {
 
 int Engine::compute_whole(const Input& in) {
   BatchCtx ctx;
+  BackGuard guard{this, &ctx};
   int rc = compute_front_noexcept(in, ctx);
   const std::string err = rc != FCS_PHMM_OK ? last_error() : std::string();
-  const int rc2 = compute_back(ctx);
+  const int rc2 = guard.finish();
   if (rc != FCS_PHMM_OK) return set_error(rc, err);
   return rc2;
 }

@@ -219,6 +219,7 @@ class Engine {
   int compute_back(BatchCtx& ctx);                    // wait until every chunk of the batch has been retired
   int compute_front_noexcept(const Input& in, BatchCtx& ctx);
   int compute_whole(const Input& in);                 // front + back
+  struct BackGuard;
   int submit(std::unique_ptr<Input> in, std::shared_ptr<void> keepalive, fcs_phmm_ticket* t);
   int wait(fcs_phmm_ticket t);
   int batch_create(const fcs_phmm_flat_batch* b, int device_index, Batch** out);

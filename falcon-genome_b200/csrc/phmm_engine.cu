@@ -2279,6 +2279,7 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
   for (const F32Range& r : P.f32) {
     max_smem = std::max(max_smem, r.smem);
     const TaskBucket& bk = s.buckets[r.bucket];
+    double r_swept = 0, r_useful = 0;
     for (const Task& t : bk.tasks) {
       const ClassDesc& cd = r.tk->classes[t.cls];
       if ((int)t.n_reads > 32 / cd.G || t.n_reads == 0 || t.n_haps == 0) return set_error(FCS_PHMM_EINVAL, "plan_check: task shape");
@@ -2299,7 +2300,12 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
       }
       swept += (pr ? 64.0 : 32.0) * cd.R * cols;
       useful += rl * hl;
+      r_swept += (pr ? 64.0 : 32.0) * cd.R * cols;
+      r_useful += rl * hl;
     }
+    if (env_i64("FCS_PHMM_DEBUG", 0))  // developer probe: where the cells of a chunk go, launch by launch
+      fprintf(stderr, "[fcs_phmm plan_check] launch tier %d form %d: %u tasks, %.3f Gcells useful, geometric efficiency %.3f\n", r.tk->tier, r.tk->form, r.n_tasks,
+              r_useful / 1e9, r_swept > 0 ? r_useful / r_swept : 1.0);
   }
   for (const RerunEntry& e2 : s.genlist) {
     const ReadMeta& m = rm[e2.read];

@@ -499,6 +499,7 @@ struct Planner {
     for (auto& b : s.buckets) { b.tasks.clear(); b.hs = 0; b.stage = 0; b.cls_mask = 0; }
     s.order.clear();
     s.ukeys.clear();
+    s.hap_order.clear();
     s.rlayout.clear();
     s.genlist.clear();
     s.gen_flags.clear();
@@ -616,7 +617,7 @@ struct Planner {
     std::vector<uint32_t> hap_len_chunk;  // by chunk-wide haplotype index
     int chunk_gcp = -2;  // -2: nothing seen yet, -1: mixed, >= 0: the one value every read shares
     size_t reads_bytes = 0, haps_bytes = 0;
-    std::vector<uint32_t> lens, hlens;
+    std::vector<uint32_t> lens, hlens, hord, hl_tmp;
     std::vector<uint64_t> sort_keys;
     size_t k = first;
     for (; k < regions.size(); ++k) {
@@ -667,6 +668,19 @@ struct Planner {
           }
         }
         hb += round_up16((uint32_t)h.len);
+      }
+      // haplotypes longest first (stable): neighbours -- the pairs of the haplotype-pair kernels -- then differ least in
+      // length, and an odd one out is the shortest.  HapMeta::col maps a packed haplotype back to the caller's column.
+      hord.resize((size_t)nh);
+      std::iota(hord.begin(), hord.end(), 0u);
+      {
+        bool sorted = true;
+        for (int32_t j = 1; j < nh && sorted; ++j) sorted = hlens[j] <= hlens[j - 1];
+        if (!sorted) {
+          std::stable_sort(hord.begin(), hord.end(), [&](uint32_t a, uint32_t b) { return hlens[a] > hlens[b]; });
+          hl_tmp.assign(hlens.begin(), hlens.begin() + nh);
+          for (int32_t j = 0; j < nh; ++j) hlens[j] = hl_tmp[hord[(size_t)j]];
+        }
       }
       const uint64_t cells = sum_r * sum_h;
       const uint64_t pairs = (uint64_t)nr * (uint64_t)nh;
@@ -870,6 +884,7 @@ struct Planner {
       }
       hap_len_chunk.insert(hap_len_chunk.end(), hlens.begin(), hlens.end());
       s.ukeys.insert(s.ukeys.end(), ukeys.begin(), ukeys.begin() + nr);
+      s.hap_order.insert(s.hap_order.end(), hord.begin(), hord.begin() + nh);
       s.rlayout.insert(s.rlayout.end(), layouts.begin(), layouts.begin() + nr);
       P.regions.push_back(g);
       P.reg_out0.push_back(P.n_pairs);
@@ -1110,16 +1125,19 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
     in.shape(g, nr, nh);
     if (nr == 0 || nh == 0) continue;
     const uint32_t hap0 = (uint32_t)hidx;
+    const uint32_t* hord = s.hap_order.data() + hidx;  // packed position -> caller's haplotype index (longest first)
     for (int32_t j = 0; j < nh; ++j) {
-      const InHap h = in.hap(g, j);
+      const uint32_t col = hord[j];
+      const InHap h = in.hap(g, (int32_t)col);
       uint8_t* dst = base + P.off_haps + hpos;
       const uint32_t lp = round_up16((uint32_t)h.len);
       copy_padded16(dst, h.b, (uint32_t)h.len, (uint8_t)'N');
-      hmeta[hidx].data_off16 = (uint32_t)(hpos / 16);
-      hmeta[hidx].len = (uint32_t)h.len;
+      hmeta[hap0 + (uint32_t)j].data_off16 = (uint32_t)(hpos / 16);
+      hmeta[hap0 + (uint32_t)j].len = (uint32_t)h.len;
+      hmeta[hap0 + (uint32_t)j].col = col;
       hpos += lp;
-      ++hidx;
     }
+    hidx += (size_t)nh;
     const uint32_t* ord = s.order.data() + opos;
     for (int32_t i = 0; i < nr; ++i) {
       const uint32_t oi = ord[i];
@@ -1815,10 +1833,10 @@ int Engine::compute_front(const Input& in, BatchCtx& ctx) {
       in.sum_lens(g, sr, sh, rc_maxrl[(size_t)g]);
       rc_cells[(size_t)g] = sr * sh;
       rc_pairs[(size_t)g] = (uint64_t)std::max(0, nr) * (uint64_t)std::max(0, nh);
-      rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 16ull * (uint64_t)std::max(0, nh);
+      rc_bytes[(size_t)g] = 5 * sr + 80ull * (uint64_t)std::max(0, nr) + sh + 20ull * (uint64_t)std::max(0, nh);
       // upper bound of the region's share of a chunk's input section: padded planes + metadata + one task and
       // one striped-path entry per pair at worst
-      rc_ub_in[(size_t)g] = 5 * sr + 91ull * (uint64_t)std::max(0, nr) + sh + 23ull * (uint64_t)std::max(0, nh) + 24ull * rc_pairs[(size_t)g];
+      rc_ub_in[(size_t)g] = 5 * sr + 91ull * (uint64_t)std::max(0, nr) + sh + 27ull * (uint64_t)std::max(0, nh) + 24ull * rc_pairs[(size_t)g];
     }
   };
   // the pass reads one length per read from the caller's (cold) arrays: for a large call it is split over the pool
@@ -2294,7 +2312,7 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
         if ((int)len + 1 > cd.G * cd.R) return set_error(FCS_PHMM_EINVAL, "plan_check: class does not cover the read");
         rl += len;
         for (uint32_t j = 0; j < t.n_haps; ++j) {
-          const uint32_t oi = m.out_off + (t.hap0 + j - m.hap0);
+          const uint32_t oi = m.out_off + hm[t.hap0 + j].col;
           if (oi >= P.n_pairs || seen[oi]++) return set_error(FCS_PHMM_EINVAL, "plan_check: pair covered twice or out of range");
         }
       }
@@ -2309,7 +2327,7 @@ int plan_check(const fcs_phmm_flat_batch* fb, int sm_count, fcs_phmm_plan_info* 
   }
   for (const RerunEntry& e2 : s.genlist) {
     const ReadMeta& m = rm[e2.read];
-    const uint32_t oi = m.out_off + (e2.hap - m.hap0);
+    const uint32_t oi = m.out_off + hm[e2.hap].col;
     if (oi >= P.n_pairs || seen[oi]++) return set_error(FCS_PHMM_EINVAL, "plan_check: generic pair covered twice or out of range");
   }
   for (uint8_t v : seen)

@@ -152,6 +152,7 @@ struct Slot {
   std::vector<TaskBucket> buckets;
   std::vector<uint32_t> order;
   std::vector<uint32_t> rlayout;       // per read (same order as ukeys): blob layout flags (phmm_types.h read_layout)
+  std::vector<uint32_t> hap_order;     // per haplotype of the chunk (region by region): the caller's index of the haplotype packed at this position
   std::vector<int> ukeys;              // per read (region by region, caller's order): gcp | ins << 8 | del << 16 if all three are constant, else -1
   std::vector<RerunEntry> genlist;     // (read, hap) pairs of the striped generic path
   std::vector<uint8_t> gen_flags;      // per chunk-wide read: takes the generic path

@@ -495,7 +495,7 @@ struct PairTile {
 // ----------------------------------------------------------------------------------------
 // result emission
 __device__ __forceinline__ void emit_f32(const KParams& p, const ReadMeta& rm, uint32_t read, uint32_t hap, float S) {
-  const uint32_t oi = rm.out_off + (hap - rm.hap0);
+  const uint32_t oi = rm.out_off + p.hmeta[hap].col;  // the caller's haplotype order
   if (p.raw_f32) p.raw_f32[oi] = S;
   if (S < 1e-28f) {  // GKL MIN_ACCEPTED: queue the pair for the double-precision kernel
     const uint32_t cls = rm.len_cls >> 24;
@@ -514,7 +514,7 @@ __device__ __forceinline__ void emit_f32(const KParams& p, const ReadMeta& rm, u
   }
 }
 __device__ __forceinline__ void emit_f64(const KParams& p, const ReadMeta& rm, uint32_t hap, double S) {
-  const uint32_t oi = rm.out_off + (hap - rm.hap0);
+  const uint32_t oi = rm.out_off + p.hmeta[hap].col;  // the caller's haplotype order
   p.out[oi] = log10(S) - 0x1.330cf3d4eda85p+8;  // log10(2^1020) as glibc rounds it (307.0505955772608)
   p.used_fp64[oi] = 1;
 }

@@ -8,7 +8,8 @@
 //             a read whose insertion, deletion and continuation qualities are each one constant
 //             (what GATK passes without BAM BI/BD tags and without the PCR indel model) is packed
 //             as TWO planes plus a 16-byte trailer [ins, del, gcp, 0...]: 2*Lp + 16 bytes
-//   haps    : per hap   bases padded to round_up(len, 16)
+//   haps    : per hap   bases padded to round_up(len, 16); the haplotypes of a region are packed longest first (pairs of
+//             neighbours then differ least in length, an odd one out is the shortest), HapMeta::col keeps the caller's index
 //   rmeta[] : ReadMeta per read,  hmeta[] : HapMeta per hap,  tasks[] : Task per CTA
 //   out[]   : double per pair, used[] : u8 per pair, raw[] : float per pair (optional)
 //   rerun[] : (read, hap) pairs queued for the double-precision kernel, one segment per
@@ -48,6 +49,7 @@ struct ReadMeta {
 struct HapMeta {
   uint32_t data_off16;
   uint32_t len;
+  uint32_t col;  // the haplotype's index in its region in the caller's order: the output column (haplotypes are packed longest first)
 };
 
 // One CTA (one warp) of the FP32 wavefront kernel: up to 32/G reads of one region

@@ -321,6 +321,77 @@ __global__ void __launch_bounds__(32, MINB) k2r(float* out, const float* in, flo
   out[blockIdx.x * 32 + threadIdx.x] = s;
 }
 
+// All-uniform form with LIGHT packing: only the two per-row operations that need no re-alignment run packed on natural
+// (even, odd) row pairs -- Y' = Y * pYY + P (FFMA2) and P' = M' * cMX (FMUL2); the M phase and the X chain stay scalar and
+// read / write the halves.  6.67 issue slots per cell instead of 7.67 (the scalar all-uniform loop is issue bound).
+template <int R, int FORM, int UNROLL, int MINB, int GW>
+__global__ void __launch_bounds__(32, MINB) kual(float* out, const float* in, float cGM, float cXX, float cMM, float cMX, int nsteps) {
+  static_assert(R % 2 == 0, "even rows per lane");
+  constexpr int TS = (((R + 3) / 4) | 1) * 4;
+  constexpr int NV = (R + 3) / 4;
+  constexpr int H = R / 2;
+  extern __shared__ __align__(16) float tab[];
+  uint32_t* hs = reinterpret_cast<uint32_t*>(tab + 5 * 32 * TS);
+  for (int i = threadIdx.x; i < 5 * 32 * TS; i += 32) tab[i] = 0.5f + 0.0001f * (i % 977);
+  for (int i = threadIdx.x; i < 1024; i += 32) hs[i] = (uint32_t)((i * 7 + 3) % 5) | ((uint32_t)((i * 11 + 1) % 5) << 16);
+  __syncwarp();
+  const float* tl = tab + threadIdx.x * TS;
+  float2 M[H], Y[H], P[H], pYY[H];
+  float X[R];
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    M[j] = make_float2(in[threadIdx.x + j], in[threadIdx.x + j + 1]);
+    Y[j] = make_float2(in[64 + threadIdx.x + j], in[65 + threadIdx.x + j]);
+    P[j] = make_float2(0.f, 0.f);
+    pYY[j] = make_float2(in[192 + j] * 0.2f, in[193 + j] * 0.21f);
+    X[2 * j] = in[32 + threadIdx.x + j]; X[2 * j + 1] = in[33 + threadIdx.x + j];
+  }
+  const float xx0 = in[250], mx0 = in[251] * 0.01f;
+  float dM = 0, dX = 0, dY = 0, acc = 0;
+  auto half = [](const float2& v, int k) { return (k & 1) ? v.y : v.x; };
+#pragma unroll(UNROLL)
+  for (int t = 0; t < nsteps; ++t) {
+    const uint32_t h2 = hs[t & 1023];
+    const float* prow = tl + (h2 & 0xffffu) * (32 * TS);
+    float pr[NV * 4];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 f = *reinterpret_cast<const float4*>(prow + v * 4);
+      pr[v * 4] = f.x; pr[v * 4 + 1] = f.y; pr[v * 4 + 2] = f.z; pr[v * 4 + 3] = f.w;
+    }
+    const float uM = __shfl_up_sync(0xffffffffu, M[H - 1].y, 1, GW), uX = __shfl_up_sync(0xffffffffu, X[R - 1], 1, GW),
+                uY = __shfl_up_sync(0xffffffffu, Y[H - 1].y, 1, GW);
+    float2 nM[H], nY[H];
+    float nX[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float md = k ? half(M[(k - 1) / 2], k - 1) : dM, xd = k ? X[k - 1] : dX, yd = k ? half(Y[(k - 1) / 2], k - 1) : dY;
+      float s = __fmul_rn(md, cMM);
+      s = __fmaf_rn(xd, cGM, s);
+      s = __fmaf_rn(yd, cGM, s);
+      const float m = __fmul_rn(s, pr[k]);
+      if (k & 1) nM[k / 2].y = m; else nM[k / 2].x = m;
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) nY[j] = __ffma2_rn(Y[j], pYY[j], P[j]);
+    nX[0] = __fmaf_rn(uX, xx0, __fmul_rn(uM, mx0));
+#pragma unroll
+    for (int j = 0; j < H; ++j) P[j] = __fmul2_rn(nM[j], bc(cMX));
+#pragma unroll
+    for (int k = 1; k < R; ++k) nX[k] = __fmaf_rn(nX[k - 1], cXX, half(P[(k - 1) / 2], k - 1));
+    acc = __fadd_rn(acc, __fadd_rn(nM[H - 1].y, nX[R - 1]));
+    dM = uM; dX = uX; dY = uY;
+#pragma unroll
+    for (int j = 0; j < H; ++j) { M[j] = nM[j]; Y[j] = nY[j]; }
+#pragma unroll
+    for (int k = 0; k < R; ++k) X[k] = nX[k];
+  }
+  float s = acc;
+#pragma unroll
+  for (int j = 0; j < H; ++j) s += M[j].x + M[j].y + Y[j].x + Y[j].y + X[2 * j] + X[2 * j + 1];
+  out[blockIdx.x * 32 + threadIdx.x] = s;
+}
+
 static int g_sel = -1, g_idx = 0;
 template <int R, int FORM, int UNROLL, int MINB, int GW, int MODE>
 void run(const char* name, int ctas_per_sm, float* out, float* in) {
@@ -330,7 +401,7 @@ void run(const char* name, int ctas_per_sm, float* out, float* in) {
   const int grid = 148 * ctas_per_sm;
   constexpr bool PACKED = MODE == 1 || MODE == 3;
   void (*kern)(float*, const float*, float, float, float, float, int);
-  if constexpr (MODE == 2) kern = krp<R, FORM, UNROLL, MINB, GW>; else if constexpr (MODE == 3) kern = k2r<R, FORM, UNROLL, MINB, GW>; else kern = k<R, FORM, UNROLL, MINB, GW, MODE == 1>;
+  if constexpr (MODE == 2) kern = krp<R, FORM, UNROLL, MINB, GW>; else if constexpr (MODE == 3) kern = k2r<R, FORM, UNROLL, MINB, GW>; else if constexpr (MODE == 4) kern = kual<R, FORM, UNROLL, MINB, GW>; else kern = k<R, FORM, UNROLL, MINB, GW, MODE == 1>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int occ = 0;
@@ -398,5 +469,12 @@ int main(int argc, char** argv) {
   run<19, 2, 2, 12, 8, 3>("two reads UA G=8", 12, out, in);
   run<19, 2, 1, 8, 8, 3>("two reads UA G=8", 8, out, in);
   run<10, 2, 2, 16, 16, 3>("two reads UA G=16", 16, out, in);
+  run<38, 2, 2, 8, 4, 4>("light-packed UA G=4", 8, out, in);
+  run<38, 2, 1, 8, 4, 4>("light-packed UA G=4", 8, out, in);
+  run<38, 2, 4, 8, 4, 4>("light-packed UA G=4", 8, out, in);
+  run<32, 2, 2, 8, 4, 4>("light-packed UA G=4", 8, out, in);
+  run<20, 2, 4, 12, 8, 4>("light-packed UA G=8", 12, out, in);
+  run<32, 2, 2, 8, 4, 0>("scalar UA G=4", 8, out, in);
+  run<20, 2, 4, 12, 8, 0>("scalar UA G=8", 12, out, in);
   return 0;
 }

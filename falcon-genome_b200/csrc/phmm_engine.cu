@@ -79,6 +79,28 @@ static inline const ClassRef* f32_class_of_len(int form, int len) { return (len 
 static inline const ClassRef* f32_coarse_class_of_len(int form, int len) { return (len >= 1 && len <= 1024) ? g_f32_coarse_by_len[form][len] : nullptr; }
 static inline int qid_of_len(int len) { return (len >= 1 && len <= 1024) ? g_qid_by_len[len] : -1; }
 
+// The regions of a chunk are visited in the chunk's order, not in memory order: every region starts with a cache miss on each
+// plane it touches (a full-size config-3 stream is 9 GB of distinct input).  Pull the first lines of the NEXT region's planes
+// while the current one is being worked on.  planes: bit 0 bases, 1 base qualities, 2 insertion, 3 deletion, 4 continuation.
+static const bool g_prefetch = env_i64("FCS_PHMM_NO_PREFETCH", 0) == 0;  // developer knob
+static inline void prefetch_region(const Input& in, int64_t g, unsigned planes, bool haps) {
+  if (!g_prefetch) return;
+  int32_t nr = 0, nh = 0;
+  in.shape(g, nr, nh);
+  if (nr > 0) {
+    const InRead r = in.read(g, 0);
+    const uint8_t* pl[5] = {r.b, r.q, r.i, r.d, r.c};
+    for (int k = 0; k < 5; ++k)
+      if ((planes >> k & 1u) && pl[k])
+        for (int off = 0; off < 256; off += 64) __builtin_prefetch(pl[k] + off, 0, 1);
+  }
+  if (haps && nh > 0) {
+    const InHap h = in.hap(g, 0);
+    if (h.b)
+      for (int off = 0; off < 256; off += 64) __builtin_prefetch(h.b + off, 0, 1);
+  }
+}
+
 // One pass over the three transition-quality planes of a read (runs once per read of every call):
 //   gcp / ins / del = the value all bytes of the plane share (masked & 127 like the kernels), or -1;
 //   same_indel      = the deletion plane equals the insertion plane byte for byte.
@@ -554,6 +576,7 @@ struct Planner {
         int32_t nr = 0, nh = 0;
         in.shape(regions[kk], nr, nh);
         qual_off[kk] = all_gcp.size();
+        if (kk + 1 < regions.size()) prefetch_region(in, regions[kk + 1], 0x1cu, false);  // ins, del, gcp
         if (nr <= 0 || nh <= 0) continue;
         for (int32_t i = 0; i < nr; ++i) {
           const InRead r = in.read(regions[kk], i);
@@ -1123,6 +1146,7 @@ int Engine::pack_chunk_static(Slot& s, const Input& in) {
     const int64_t g = P.regions[k];
     int32_t nr = 0, nh = 0;
     in.shape(g, nr, nh);
+    if (k + 1 < P.regions.size()) prefetch_region(in, P.regions[k + 1], 0x1fu, true);  // every plane that may be copied + haplotypes
     if (nr == 0 || nh == 0) continue;
     const uint32_t hap0 = (uint32_t)hidx;
     const uint32_t* hord = s.hap_order.data() + hidx;  // packed position -> caller's haplotype index (longest first)

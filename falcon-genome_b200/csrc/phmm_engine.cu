@@ -1940,17 +1940,19 @@ int Engine::compute_front(const Input& in, BatchCtx& ctx) {
     for (int64_t g : part[d]) {
       const size_t k = (size_t)g;
       static const int ramp_style = (int)env_i64("FCS_PHMM_RAMP", 2);
+      static const int64_t ramp_floor = env_i64("FCS_PHMM_RAMP_FLOOR_CELLS", 125000000LL);  // developer knob: smallest ramp chunk
+      static const int64_t ramp0_div = std::max<int64_t>(1, env_i64("FCS_PHMM_RAMP0_DIV", 4));  // developer knob: first round = limit / this
       int64_t lim_now = limit;
       // ramp: the first round of chunks (one per packing thread) is small so that the device starts after a fraction of
       // a millisecond of planning + packing, later rounds double.  Style 2 adds a round at 1/16 for calls whose regular
       // chunk is large (config 3: 3 Gcells = 1.1 ms of host work before the first launch otherwise).
       const int round = (int)chunks.size() / sched_threads;
       if (ramp && ramp_style == 2 && limit >= 1500000000LL) {
-        if (round == 0) lim_now = std::max<int64_t>(limit / 16, 125000000LL);
-        else if (round == 1) lim_now = std::max<int64_t>(limit / 4, 125000000LL);
-        else if (round == 2) lim_now = std::max<int64_t>(limit / 2, 125000000LL);
-      } else if (ramp && round == 0) lim_now = std::max<int64_t>(limit / 4, 125000000LL);
-      else if (ramp && ramp_style >= 1 && round == 1) lim_now = std::max<int64_t>(limit / 2, 125000000LL);
+        if (round == 0) lim_now = std::max<int64_t>(limit / 16, ramp_floor);
+        else if (round == 1) lim_now = std::max<int64_t>(limit / 4, ramp_floor);
+        else if (round == 2) lim_now = std::max<int64_t>(limit / 2, ramp_floor);
+      } else if (ramp && round == 0) lim_now = std::max<int64_t>(limit / ramp0_div, ramp_floor);
+      else if (ramp && ramp_style >= 1 && round == 1) lim_now = std::max<int64_t>(limit / 2, ramp_floor);
       if (!cur.empty() && cells > 0 &&
           ((int64_t)(cells + rc_cells[k]) > lim_now || pairs + rc_pairs[k] > 0x7fffffffULL || bytes + rc_bytes[k] > (1ull << 31))) {
         chunks.emplace_back(std::move(cur));

@@ -159,7 +159,11 @@ FCS_PHMM_API int fcs_pairhmm_device_count(const fcs_phmm_handle* h);
 /* ---- the reference-facing call -------------------------------------------------------
  * Blocking; many regions per call (one region = one GKL computeLikelihoodsNative).  Packs
  * the caller's host arrays, partitions regions over the handle's devices by cell count,
- * runs H2D -> FP32 wavefront -> FP64 rerun -> D2H per chunk and scatters into out_log10. */
+ * runs H2D -> FP32 wavefront -> FP64 rerun -> D2H per chunk and scatters into out_log10.
+ * Thread-safe on one handle (GATK's --native-pair-hmm-threads, /root/reference/src/workers/HTCWorker.cpp:85): calls that arrive
+ * while a batch is being planned are merged into the next batch, and a batch is planned and packed while the previous one's last
+ * chunks are still on the devices.  The caller's arrays must stay untouched until its own call returns; an input the batcher
+ * refuses fails only the call that carried it. */
 FCS_PHMM_API int fcs_pairhmm_compute(fcs_phmm_handle* h, const fcs_phmm_region* regions, int32_t n_regions);
 /* Same work from the flat layout.  used_fp64 and raw_f32 may be NULL; raw_f32 needs keep_raw_f32. */
 FCS_PHMM_API int fcs_pairhmm_compute_flat(fcs_phmm_handle* h, const fcs_phmm_flat_batch* b, double* out, uint8_t* used_fp64,

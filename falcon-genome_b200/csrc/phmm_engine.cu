@@ -629,7 +629,7 @@ struct Planner {
       }
     }
     static const double tail1_x = (double)env_i64("FCS_PHMM_TAIL1_X100", 150) / 100.0;  // in waves: half-length tasks
-    static const double tail2_x = (double)env_i64("FCS_PHMM_TAIL2_X100", 50) / 100.0;   // in waves: wide lane groups, one haplotype
+    static const double tail2_x = (double)env_i64("FCS_PHMM_TAIL2_X100", 25) / 100.0;   // in waves: wide lane groups, one haplotype (0.5 before the pair kernels: their tasks are twice as long, the scalar wide tasks cost more against them; config 1 +4 %)
     static const int tail2_g = (int)env_i64("FCS_PHMM_TAIL2_G", 16);
     const uint64_t wave_pairs = (uint64_t)sm_count * 64u;
     std::vector<uint32_t> f64_cap((size_t)f64_queue_count(), 0), f64_maxlh((size_t)f64_queue_count(), 0);
@@ -788,7 +788,8 @@ struct Planner {
         }
         if (ku) k0 = ku;
         // Haplotype-pair form: reads with one gap-continuation quality against two haplotypes at a time in packed
-        // f32x2 arithmetic.  Throughput policy only; an odd haplotype is left to the scalar uniform-GCP class.
+        // f32x2 arithmetic.  Throughput policy only (pair classes on wide lane groups for the tail window were measured:
+        // config 3 -1.4 %, config 2 -1 %); an odd haplotype is left to the scalar uniform-GCP class.
         static const bool pairs_enabled = env_i64("FCS_PHMM_NO_PAIRS", 0) == 0;  // developer knob
         const ClassRef* kp = nullptr;
         if (!ku && !wide_G && pairs_enabled && nh >= 2 && gcps[ord[i]] >= 0) {
